@@ -1,0 +1,202 @@
+// blend_bwd.cu -- per-tile back-to-front gradient blend for sm_100a.
+//
+// Behavioural spec: DGR/cuda_rasterizer/backward.cu:428-581 (renderCUDA backward): per pixel,
+// walk the tile's instance list from its last contributor backwards, rebuild T by division,
+// accumulate dL/dcolor, dL/dalpha (recursive accum_rec + background term), and from it
+// dL/dmean2D (x,y), dL/dconic (x,y,w), dL/dopacity for every contributing (pixel, Gaussian)
+// pair.  The reference issues 9 scalar atomicAdd per pair.
+//
+// B200 design: same TMA-staged 2-stage ring as the forward (batches taken from the END of
+// the tile's contiguous record slice), same per-warp sub-rectangle cull, records beyond the
+// warp's furthest last-contributor are never touched.  Per surviving record the 9 partial
+// gradients are reduced across the warp's 32 pixels with shuffles and leave the SM as three
+// 16-byte vector reductions (red.global.add.v4.f32 -> REDG.E.ADD.F32x4) from one lane into a
+// 48-byte per-Gaussian accumulator: 3 L2 reduction ops per (warp, Gaussian) instead of
+// 9 x (number of contributing pixels).
+#include "blend_common.cuh"
+#include "gcr_kernels.h"
+
+namespace {
+
+__forceinline__ __device__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(kBlendThreads)
+blend_bwd_kernel(GcrBlendArgs a) {
+  __shared__ __align__(128) GcrRecord stage[kBlendStages][kBlendBatch];
+  __shared__ __align__(8) uint64_t full_bar[kBlendStages];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tile_x = blockIdx.x;
+  const int tile_y = a.shard_rank + (int)blockIdx.y * a.shard_count;
+  const uint2 range = a.ranges[tile_y * a.grid_x + tile_x];
+  const int n = (int)(range.y - range.x);
+
+  const int sub_x0 = tile_x * GCR_TILE_X + (warp & 1) * 8;
+  const int sub_y0 = tile_y * GCR_TILE_Y + (warp >> 1) * 4;
+  const int pix_x = sub_x0 + (lane & 7);
+  const int pix_y = sub_y0 + (lane >> 3);
+  const bool inside = pix_x < a.W && pix_y < a.H;
+  const float pxf = (float)pix_x, pyf = (float)pix_y;
+  const float rx0 = (float)sub_x0, rx1 = (float)(sub_x0 + 7);
+  const float ry0 = (float)sub_y0, ry1 = (float)(sub_y0 + 3);
+  const int pix_id = a.W * pix_y + pix_x;
+  const size_t plane = (size_t)a.H * a.W;
+
+  const float T_final = inside ? a.final_T[pix_id] : 0.f;
+  const int last_contributor = inside ? (int)a.n_contrib[pix_id] : 0;
+  float dLp0 = 0.f, dLp1 = 0.f, dLp2 = 0.f;
+  if (inside) {
+    dLp0 = a.dL_dpix[pix_id];
+    dLp1 = a.dL_dpix[plane + pix_id];
+    dLp2 = a.dL_dpix[2 * plane + pix_id];
+  }
+  const float bg_dot_dpixel = a.bg[0] * dLp0 + a.bg[1] * dLp1 + a.bg[2] * dLp2;
+
+  // Only list positions <= the furthest last contributor of the CTA matter at all.
+  __shared__ int s_max_last;
+  if (tid == 0) {
+    s_max_last = 0;
+    gcr_mbar_init(&full_bar[0], 1);
+    gcr_mbar_init(&full_bar[1], 1);
+    gcr_mbar_fence_init();
+  }
+  __syncthreads();
+  int warp_last = last_contributor;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, o));
+  if (lane == 0 && warp_last > 0) atomicMax(&s_max_last, warp_last);
+  __syncthreads();
+  const int m = min(n, s_max_last);  // records [0, m) of the tile slice are relevant
+  const int nb = (m + kBlendBatch - 1) / kBlendBatch;
+
+  const GcrRecord* __restrict__ src = a.inst + range.x;
+  // batch b (b = 0 is the LAST one) covers list indices [lo_b, hi_b), hi_b = m - b*BATCH
+  if (tid == 0 && nb > 0) {
+    const int hi = m, lo = max(0, hi - kBlendBatch);
+    const uint32_t bytes = (uint32_t)(hi - lo) * (uint32_t)sizeof(GcrRecord);
+    gcr_mbar_expect_tx(&full_bar[0], bytes);
+    gcr_bulk_g2s(&stage[0][0], src + lo, bytes, &full_bar[0]);
+  }
+
+  float T = T_final;
+  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;       // accum_rec
+  float last_alpha = 0.f;
+  float lc0 = 0.f, lc1 = 0.f, lc2 = 0.f;          // last_color
+  const float ddelx_dx = 0.5f * a.W;
+  const float ddely_dy = 0.5f * a.H;
+
+  for (int b = 0; b < nb; ++b) {
+    const int s = b & 1;
+    if (tid == 0 && b + 1 < nb) {
+      const int hi = m - (b + 1) * kBlendBatch, lo = max(0, hi - kBlendBatch);
+      const uint32_t bytes = (uint32_t)(hi - lo) * (uint32_t)sizeof(GcrRecord);
+      gcr_mbar_expect_tx(&full_bar[s ^ 1], bytes);
+      gcr_bulk_g2s(&stage[s ^ 1][0], src + lo, bytes, &full_bar[s ^ 1]);
+    }
+    gcr_mbar_wait(&full_bar[s], (uint32_t)((b >> 1) & 1));
+
+    const int hi = m - b * kBlendBatch, lo = max(0, hi - kBlendBatch);
+    const int cnt = hi - lo;
+    const GcrRecord* __restrict__ st = stage[s];
+    // list index of st[j] is lo + j; 1-based position = lo + j + 1
+    if (warp_last > lo) {
+      for (int g0 = ((cnt - 1) >> 5) << 5; g0 >= 0; g0 -= 32) {
+        if (lo + g0 >= warp_last) continue;  // whole group behind every pixel's last contributor
+        const int j = g0 + lane;
+        bool touch = false;
+        if (j < cnt && lo + j < warp_last) {
+          const float4 q0 = st[j].q0;
+          const float2 q1 = *reinterpret_cast<const float2*>(&st[j].q1);
+          const float twoL = st[j].q2.z;
+          touch = gcr_subrect_touch(q0.x, q0.y, q0.z, q0.w, q1.x, twoL, rx0, rx1, ry0, ry1);
+        }
+        unsigned mask = __ballot_sync(0xffffffffu, touch);
+        while (mask) {
+          const int bit = 31 - __clz(mask);
+          mask &= ~(1u << bit);
+          const int jj = g0 + bit;
+          const float4 r0 = st[jj].q0;
+          const float4 r1 = st[jj].q1;
+          const float4 r2 = st[jj].q2;
+          float g_mx = 0.f, g_my = 0.f, g_ca = 0.f, g_cb = 0.f, g_cc = 0.f, g_op = 0.f;
+          float g_r = 0.f, g_g = 0.f, g_b = 0.f;
+          bool contrib = false;
+          // reference: contributor-- ; if (contributor >= last_contributor) continue;
+          if (lo + jj < last_contributor) {
+            const float dx = __fsub_rn(r0.x, pxf);
+            const float dy = __fsub_rn(r0.y, pyf);
+            const float power = gcr_power(dx, dy, r0.z, r0.w, r1.x);
+            if (!(power > 0.0f)) {
+              const float G = expf(power);
+              const float alpha = fminf(0.99f, __fmul_rn(r1.y, G));
+              if (!(alpha < 1.0f / 255.0f)) {
+                contrib = true;
+                T = T / (1.f - alpha);
+                const float dchannel_dcolor = alpha * T;
+                float dL_dalpha = 0.f;
+                acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0;
+                lc0 = r1.z;
+                dL_dalpha += (r1.z - acc0) * dLp0;
+                g_r = dchannel_dcolor * dLp0;
+                acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1;
+                lc1 = r1.w;
+                dL_dalpha += (r1.w - acc1) * dLp1;
+                g_g = dchannel_dcolor * dLp1;
+                acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2;
+                lc2 = r2.x;
+                dL_dalpha += (r2.x - acc2) * dLp2;
+                g_b = dchannel_dcolor * dLp2;
+                dL_dalpha *= T;
+                last_alpha = alpha;
+                dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+
+                const float dL_dG = r1.y * dL_dalpha;
+                const float gdx = G * dx;
+                const float gdy = G * dy;
+                const float dG_ddelx = -gdx * r0.z - gdy * r0.w;
+                const float dG_ddely = -gdy * r1.x - gdx * r0.w;
+                g_mx = dL_dG * dG_ddelx * ddelx_dx;
+                g_my = dL_dG * dG_ddely * ddely_dy;
+                g_ca = -0.5f * gdx * dx * dL_dG;
+                g_cb = -0.5f * gdx * dy * dL_dG;
+                g_cc = -0.5f * gdy * dy * dL_dG;
+                g_op = G * dL_dalpha;
+              }
+            }
+          }
+          if (__ballot_sync(0xffffffffu, contrib) != 0u) {
+            g_mx = warp_sum(g_mx);
+            g_my = warp_sum(g_my);
+            g_ca = warp_sum(g_ca);
+            g_cb = warp_sum(g_cb);
+            g_cc = warp_sum(g_cc);
+            g_op = warp_sum(g_op);
+            g_r = warp_sum(g_r);
+            g_g = warp_sum(g_g);
+            g_b = warp_sum(g_b);
+            if (lane == 0) {
+              GcrGradAcc* dst = a.grad_acc + __float_as_uint(r2.y);
+              gcr_red_add_v4(&dst->g0, g_mx, g_my, g_ca, g_cb);
+              gcr_red_add_v4(&dst->g1, g_cc, g_op, g_r, g_g);
+              atomicAdd(&dst->g2.x, g_b);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();  // stage s may be refilled at the top of iteration b+2
+  }
+}
+
+}  // namespace
+
+void gcr_launch_blend_bwd(const GcrBlendArgs& a, cudaStream_t stream) {
+  const int rows = (a.grid_y - a.shard_rank + a.shard_count - 1) / a.shard_count;
+  if (rows <= 0 || a.grid_x <= 0) return;
+  dim3 grid(a.grid_x, rows, 1);
+  blend_bwd_kernel<<<grid, kBlendThreads, 0, stream>>>(a);
+}

@@ -1,0 +1,151 @@
+// blend_fwd.cu -- per-tile front-to-back alpha composition for sm_100a.
+//
+// Behavioural spec: DGR/cuda_rasterizer/forward.cu:238-346 (renderCUDA): per pixel, walk the
+// tile's depth-sorted instance list; d = mean2D - pix; power = -1/2 (A dx^2 + C dy^2) - B dx dy;
+// skip power > 0; alpha = min(0.99, o exp(power)); skip alpha < 1/255; stop when
+// T (1 - alpha) < 1e-4; C += rgb alpha T.  Outputs colour (CHW) = C + T bg, final_T, n_contrib
+// (1-based list position of the last contributor).
+//
+// B200 design (not the reference's): the tile's instance records are contiguous in HBM
+// (binning.cu gathers them in sorted order), so each batch of 256 records (12 KB) is staged
+// into shared memory by ONE TMA bulk copy (cp.async.bulk -> UBLKCP) into a 2-stage ring that
+// is refilled while the previous batch is being blended (mbarrier complete_tx signalling, no
+// per-thread gather loads).  Each warp owns an 8x4 pixel sub-rectangle: lanes first test 32
+// records at a time against that sub-rectangle (exact-conservative ellipse/rect test,
+// blend_common.cuh), ballot, and only the surviving records are evaluated per pixel.  A warp
+// whose 32 pixels have all saturated (T < 1e-4) stops evaluating; the CTA leaves when all
+// eight have (block vote once per batch).  Arithmetic per pixel is pinned to the reference's
+// SASS order (gcr_power, expf, fma order of the colour accumulation), so final_T / n_contrib
+// are bit-identical.
+#include "blend_common.cuh"
+#include "gcr_kernels.h"
+
+namespace {
+
+__global__ void __launch_bounds__(kBlendThreads)
+blend_fwd_kernel(GcrBlendArgs a) {
+  __shared__ __align__(128) GcrRecord stage[kBlendStages][kBlendBatch];
+  __shared__ __align__(8) uint64_t full_bar[kBlendStages];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tile_x = blockIdx.x;
+  const int tile_y = a.shard_rank + (int)blockIdx.y * a.shard_count;
+  const uint2 range = a.ranges[tile_y * a.grid_x + tile_x];
+  const int n = (int)(range.y - range.x);
+  const int nb = (n + kBlendBatch - 1) / kBlendBatch;
+
+  const int sub_x0 = tile_x * GCR_TILE_X + (warp & 1) * 8;
+  const int sub_y0 = tile_y * GCR_TILE_Y + (warp >> 1) * 4;
+  const int pix_x = sub_x0 + (lane & 7);
+  const int pix_y = sub_y0 + (lane >> 3);
+  const bool inside = pix_x < a.W && pix_y < a.H;
+  const float pxf = (float)pix_x, pyf = (float)pix_y;
+  const float rx0 = (float)sub_x0, rx1 = (float)(sub_x0 + 7);
+  const float ry0 = (float)sub_y0, ry1 = (float)(sub_y0 + 3);
+
+  if (tid == 0) {
+    gcr_mbar_init(&full_bar[0], 1);
+    gcr_mbar_init(&full_bar[1], 1);
+    gcr_mbar_fence_init();
+  }
+  __syncthreads();
+
+  const GcrRecord* __restrict__ src = a.inst + range.x;
+  int issued = 0;
+  if (tid == 0 && nb > 0) {
+    const uint32_t bytes = (uint32_t)min(kBlendBatch, n) * (uint32_t)sizeof(GcrRecord);
+    gcr_mbar_expect_tx(&full_bar[0], bytes);
+    gcr_bulk_g2s(&stage[0][0], src, bytes, &full_bar[0]);
+    issued = 1;
+  }
+
+  float T = 1.0f;
+  float C0 = 0.f, C1 = 0.f, C2 = 0.f;
+  uint32_t last_contributor = 0;
+  bool done = !inside;
+
+  int b = 0;
+  for (; b < nb; ++b) {
+    const int s = b & 1;
+    if (tid == 0 && b + 1 < nb) {
+      // stage s^1 was last read in iteration b-1; the vote barrier at its end ordered those reads
+      const int start = (b + 1) * kBlendBatch;
+      const uint32_t bytes = (uint32_t)min(kBlendBatch, n - start) * (uint32_t)sizeof(GcrRecord);
+      gcr_mbar_expect_tx(&full_bar[s ^ 1], bytes);
+      gcr_bulk_g2s(&stage[s ^ 1][0], src + start, bytes, &full_bar[s ^ 1]);
+      issued = b + 2;
+    }
+    gcr_mbar_wait(&full_bar[s], (uint32_t)((b >> 1) & 1));
+
+    const int cnt = min(kBlendBatch, n - b * kBlendBatch);
+    const GcrRecord* __restrict__ st = stage[s];
+    if (__ballot_sync(0xffffffffu, !done) != 0u) {
+      for (int g0 = 0; g0 < cnt; g0 += 32) {
+        const int j = g0 + lane;
+        bool touch = false;
+        if (j < cnt) {
+          const float4 q0 = st[j].q0;
+          const float2 q1 = *reinterpret_cast<const float2*>(&st[j].q1);
+          const float twoL = st[j].q2.z;
+          touch = gcr_subrect_touch(q0.x, q0.y, q0.z, q0.w, q1.x, twoL, rx0, rx1, ry0, ry1);
+        }
+        unsigned mask = __ballot_sync(0xffffffffu, touch);
+        while (mask) {
+          const int jj = g0 + __ffs(mask) - 1;
+          mask &= mask - 1;
+          const float4 r0 = st[jj].q0;   // x, y, A, B   (broadcast LDS.128)
+          const float4 r1 = st[jj].q1;   // C, o, r, g
+          const float cb = st[jj].q2.x;  // b
+          if (!done) {
+            const float dx = __fsub_rn(r0.x, pxf);
+            const float dy = __fsub_rn(r0.y, pyf);
+            const float power = gcr_power(dx, dy, r0.z, r0.w, r1.x);
+            if (!(power > 0.0f)) {
+              const float alpha = fminf(0.99f, __fmul_rn(r1.y, expf(power)));
+              if (!(alpha < 1.0f / 255.0f)) {
+                const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+                if (test_T < 0.0001f) {
+                  done = true;
+                } else {
+                  C0 = __fmaf_rn(T, __fmul_rn(alpha, r1.z), C0);
+                  C1 = __fmaf_rn(T, __fmul_rn(alpha, r1.w), C1);
+                  C2 = __fmaf_rn(T, __fmul_rn(alpha, cb), C2);
+                  T = test_T;
+                  last_contributor = (uint32_t)(b * kBlendBatch + jj + 1);
+                }
+              }
+            }
+          }
+        }
+        if (__ballot_sync(0xffffffffu, !done) == 0u) break;  // warp saturated
+      }
+    }
+    // CTA vote: everyone saturated -> leave; also fences this batch's smem reads before the
+    // stage is refilled two iterations later.
+    if (__syncthreads_count(done) == kBlendThreads) {
+      ++b;
+      break;
+    }
+  }
+  // never exit with a bulk copy still in flight into this CTA's shared memory
+  if (tid == 0 && issued > b) gcr_mbar_wait(&full_bar[b & 1], (uint32_t)((b >> 1) & 1));
+
+  if (inside) {
+    const int pix_id = a.W * pix_y + pix_x;
+    const size_t plane = (size_t)a.H * a.W;
+    a.final_T[pix_id] = T;
+    a.n_contrib[pix_id] = last_contributor;
+    a.out_color[pix_id] = __fmaf_rn(T, a.bg[0], C0);
+    a.out_color[plane + pix_id] = __fmaf_rn(T, a.bg[1], C1);
+    a.out_color[2 * plane + pix_id] = __fmaf_rn(T, a.bg[2], C2);
+  }
+}
+
+}  // namespace
+
+void gcr_launch_blend_fwd(const GcrBlendArgs& a, cudaStream_t stream) {
+  const int rows = (a.grid_y - a.shard_rank + a.shard_count - 1) / a.shard_count;
+  if (rows <= 0 || a.grid_x <= 0) return;
+  dim3 grid(a.grid_x, rows, 1);
+  blend_fwd_kernel<<<grid, kBlendThreads, 0, stream>>>(a);
+}

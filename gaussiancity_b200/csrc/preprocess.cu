@@ -1,0 +1,286 @@
+// preprocess.cu -- per-Gaussian forward preprocessing for sm_100a.
+//
+// Behavioural spec: DGR/cuda_rasterizer/forward.cu:147-233 (preprocessCUDA) with
+// in_frustum (auxiliary.h:132-156), computeCov3D (forward.cu:110-144), computeCov2D
+// (forward.cu:69-105), computeColorFromSH (forward.cu:20-66), ndc2Pix/getRect
+// (auxiliary.h:32-46).  radii / tiles_touched / depth / mean2D / conic feed integer work that
+// must be bit-exact with the reference extension, so every rounding on that path is pinned
+// with explicit _rn intrinsics in the order nvcc 12.9 contracts the reference expressions
+// (a*b + c*d + e*f  ->  fma(e,f, fma(a,b, rn(c*d))); see DESIGN.md "bit-exactness").
+//
+// Layout differences from the reference (free to choose): outputs go to one
+// 48-byte record per Gaussian (GcrRecord) + a depth key array + a packed clamp byte; cov3D is
+// not stored (the backward recomputes it) unless a debug pointer is given.
+#include <cstdio>
+#include "gcr_common.cuh"
+#include "gcr_kernels.h"
+
+namespace {
+
+// rn(a*b + c*d + e*f) in the contraction order nvcc uses for GLM's mat3 products.
+__forceinline__ __device__ float dot3(float a, float b, float c, float d, float e, float f) {
+  return __fmaf_rn(e, f, __fmaf_rn(a, b, __fmul_rn(c, d)));
+}
+// m[k]*x + m[4+k]*y + m[8+k]*z (+ m[12+k]) as auxiliary.h:48-66 compiles.
+__forceinline__ __device__ float xf3(const float* __restrict__ m, int k, float x, float y,
+                                     float z) {
+  return __fmaf_rn(z, m[8 + k], __fmaf_rn(x, m[k], __fmul_rn(y, m[4 + k])));
+}
+
+struct ShardInfo {
+  int rank, count;
+};
+// number of tile rows r in [y0, y1) with r % count == rank
+__forceinline__ __device__ int owned_rows(int y0, int y1, int rank, int count) {
+  if (count <= 1) return y1 - y0;
+  if (y1 <= y0) return 0;
+  // rows < y with r%count==rank : (y - rank + count - 1) / count  for y >= 0
+  auto below = [&](int y) { return (y - rank + count - 1) / count; };
+  return max(0, below(y1)) - max(0, below(y0));
+}
+
+template <bool kHasSH>
+__global__ void __launch_bounds__(256)
+preprocess_fwd_kernel(GcrPreprocessArgs a) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.P) return;
+
+  // Defaults for culled Gaussians.
+  int radius_out = 0;
+  uint32_t tiles = 0;
+  uint32_t depth_key = 0xFFFFFFFFu;  // sorts behind every visible Gaussian
+
+  const float px = a.means3D[3 * idx + 0];
+  const float py = a.means3D[3 * idx + 1];
+  const float pz = a.means3D[3 * idx + 2];
+
+  const float* __restrict__ V = a.viewmatrix;
+  const float* __restrict__ PM = a.projmatrix;
+
+  // in_frustum: view-space depth test (auxiliary.h:141-154)
+  const float vz = __fadd_rn(xf3(V, 2, px, py, pz), V[14]);
+  bool visible = vz > 0.2f;
+  if (!visible && a.prefiltered) {
+    printf("Point is filtered although prefiltered is set. This shouldn't happen!");
+    __trap();
+  }
+
+  if (visible) {
+    // clip-space projection (forward.cu:179-181)
+    const float hx = __fadd_rn(xf3(PM, 0, px, py, pz), PM[12]);
+    const float hy = __fadd_rn(xf3(PM, 1, px, py, pz), PM[13]);
+    const float hw = __fadd_rn(xf3(PM, 3, px, py, pz), PM[15]);
+    const float p_w = 1.0f / __fadd_rn(hw, 0.0000001f);
+    const float ndc_x = __fmul_rn(hx, p_w);
+    const float ndc_y = __fmul_rn(hy, p_w);
+
+    // 3D covariance (forward.cu:110-144) -- quaternion deliberately NOT normalised.
+    float c0, c1, c2, c3, c4, c5;
+    if (a.cov3D_precomp != nullptr) {
+      const float* c = a.cov3D_precomp + 6 * (size_t)idx;
+      c0 = c[0]; c1 = c[1]; c2 = c[2]; c3 = c[3]; c4 = c[4]; c5 = c[5];
+    } else {
+      const float s0 = __fmul_rn(a.scale_modifier, a.scales[3 * idx + 0]);
+      const float s1 = __fmul_rn(a.scale_modifier, a.scales[3 * idx + 1]);
+      const float s2 = __fmul_rn(a.scale_modifier, a.scales[3 * idx + 2]);
+      const float4 q = reinterpret_cast<const float4*>(a.rotations)[idx];
+      const float r = q.x, x = q.y, y = q.z, z = q.w;
+      // R columns (GLM column-major constructor order)
+      const float R00 = __fsub_rn(1.f, __fmul_rn(2.f, __fmaf_rn(y, y, __fmul_rn(z, z))));
+      const float R01 = __fmul_rn(2.f, __fmaf_rn(x, y, -__fmul_rn(r, z)));
+      const float R02 = __fmul_rn(2.f, __fmaf_rn(x, z, __fmul_rn(r, y)));
+      const float R10 = __fmul_rn(2.f, __fmaf_rn(x, y, __fmul_rn(r, z)));
+      const float R11 = __fsub_rn(1.f, __fmul_rn(2.f, __fmaf_rn(x, x, __fmul_rn(z, z))));
+      const float R12 = __fmul_rn(2.f, __fmaf_rn(y, z, -__fmul_rn(r, x)));
+      const float R20 = __fmul_rn(2.f, __fmaf_rn(x, z, -__fmul_rn(r, y)));
+      const float R21 = __fmul_rn(2.f, __fmaf_rn(y, z, __fmul_rn(r, x)));
+      const float R22 = __fsub_rn(1.f, __fmul_rn(2.f, __fmaf_rn(x, x, __fmul_rn(y, y))));
+      // M = S * R  ->  M[i][j] = s_j * R[i][j]   (column i, row j)
+      const float M00 = __fmul_rn(s0, R00), M01 = __fmul_rn(s1, R01), M02 = __fmul_rn(s2, R02);
+      const float M10 = __fmul_rn(s0, R10), M11 = __fmul_rn(s1, R11), M12 = __fmul_rn(s2, R12);
+      const float M20 = __fmul_rn(s0, R20), M21 = __fmul_rn(s1, R21), M22 = __fmul_rn(s2, R22);
+      // Sigma = M^T M : Sigma[i][j] = M[j][0]*M[i][0] + M[j][1]*M[i][1] + M[j][2]*M[i][2]
+      c0 = dot3(M00, M00, M01, M01, M02, M02);
+      c1 = dot3(M10, M00, M11, M01, M12, M02);
+      c2 = dot3(M20, M00, M21, M01, M22, M02);
+      c3 = dot3(M10, M10, M11, M11, M12, M12);
+      c4 = dot3(M20, M10, M21, M11, M22, M12);
+      c5 = dot3(M20, M20, M21, M21, M22, M22);
+    }
+    if (a.dbg_cov3D != nullptr) {
+      float* c = a.dbg_cov3D + 6 * (size_t)idx;
+      c[0] = c0; c[1] = c1; c[2] = c2; c[3] = c3; c[4] = c4; c[5] = c5;
+    }
+
+    // 2D covariance (forward.cu:69-105), EWA splatting with clamped view-space x/z, y/z.
+    float tx = __fadd_rn(xf3(V, 0, px, py, pz), V[12]);
+    float ty = __fadd_rn(xf3(V, 1, px, py, pz), V[13]);
+    const float tz = vz;
+    const float limx = __fmul_rn(1.3f, a.tan_fovx);
+    const float limy = __fmul_rn(1.3f, a.tan_fovy);
+    const float txtz = tx / tz;
+    const float tytz = ty / tz;
+    tx = __fmul_rn(fminf(limx, fmaxf(-limx, txtz)), tz);
+    ty = __fmul_rn(fminf(limy, fmaxf(-limy, tytz)), tz);
+    const float tz2 = __fmul_rn(tz, tz);
+    const float J00 = a.focal_x / tz;
+    const float J02 = -__fmul_rn(a.focal_x, tx) / tz2;
+    const float J11 = a.focal_y / tz;
+    const float J12 = -__fmul_rn(a.focal_y, ty) / tz2;
+    // T = W * J with W[k][j] = V[4*j + k]; T[0][j] = fma(W2j,J02, rn(W0j*J00)),
+    // T[1][j] = fma(W2j,J12, rn(W1j*J11)), T[2][j] = 0.
+    const float T00 = __fmaf_rn(V[2], J02, __fmul_rn(V[0], J00));
+    const float T01 = __fmaf_rn(V[6], J02, __fmul_rn(V[4], J00));
+    const float T02 = __fmaf_rn(V[10], J02, __fmul_rn(V[8], J00));
+    const float T10 = __fmaf_rn(V[2], J12, __fmul_rn(V[1], J11));
+    const float T11 = __fmaf_rn(V[6], J12, __fmul_rn(V[5], J11));
+    const float T12 = __fmaf_rn(V[10], J12, __fmul_rn(V[9], J11));
+    // X = T^T * Vrk^T : X[i][j] = T[j][0]*S(i,0) + T[j][1]*S(i,1) + T[j][2]*S(i,2)
+    const float X00 = dot3(T00, c0, T01, c1, T02, c2);
+    const float X10 = dot3(T00, c1, T01, c3, T02, c4);
+    const float X20 = dot3(T00, c2, T01, c4, T02, c5);
+    const float X01 = dot3(T10, c0, T11, c1, T12, c2);
+    const float X11 = dot3(T10, c1, T11, c3, T12, c4);
+    const float X21 = dot3(T10, c2, T11, c4, T12, c5);
+    // cov = X * T : cov[i][j] = X[0][j]*T[i][0] + X[1][j]*T[i][1] + X[2][j]*T[i][2]
+    float cov_x = dot3(X00, T00, X10, T01, X20, T02);
+    const float cov_y = dot3(X01, T00, X11, T01, X21, T02);
+    float cov_z = dot3(X01, T10, X11, T11, X21, T12);
+    cov_x = __fadd_rn(cov_x, 0.3f);
+    cov_z = __fadd_rn(cov_z, 0.3f);
+
+    // conic = inverse (forward.cu:196-201)
+    const float det = __fmaf_rn(cov_x, cov_z, -__fmul_rn(cov_y, cov_y));
+    if (det != 0.0f) {
+      const float det_inv = 1.f / det;
+      const float conic_x = __fmul_rn(cov_z, det_inv);
+      const float conic_y = __fmul_rn(cov_y, -det_inv);
+      const float conic_z = __fmul_rn(cov_x, det_inv);
+
+      // screen-space extent (forward.cu:203-215)
+      const float mid = __fmul_rn(0.5f, __fadd_rn(cov_x, cov_z));
+      const float sq = sqrtf(fmaxf(0.1f, __fmaf_rn(mid, mid, -det)));
+      const float lambda1 = __fadd_rn(mid, sq);
+      const float lambda2 = __fsub_rn(mid, sq);
+      const float my_radius = ceilf(__fmul_rn(3.f, sqrtf(fmaxf(lambda1, lambda2))));
+      const float pix_x = gcr_ndc2pix(ndc_x, a.W);
+      const float pix_y = gcr_ndc2pix(ndc_y, a.H);
+      uint2 rmin, rmax;
+      gcr_get_rect(pix_x, pix_y, (int)my_radius, a.grid_x, a.grid_y, rmin, rmax);
+      const uint32_t touched = (rmax.x - rmin.x) * (rmax.y - rmin.y);
+      if (touched != 0) {
+        // colour: SH evaluation (forward.cu:20-66) or precomputed
+        float cr, cg, cb;
+        if (kHasSH) {
+          const float dx = __fsub_rn(px, a.campos[0]);
+          const float dy = __fsub_rn(py, a.campos[1]);
+          const float dz = __fsub_rn(pz, a.campos[2]);
+          const float len = sqrtf(dot3(dx, dx, dy, dy, dz, dz));
+          const float x = dx / len, y = dy / len, z = dz / len;
+          const float4* __restrict__ sh4 =
+              reinterpret_cast<const float4*>(a.shs + (size_t)idx * a.M * 3);
+          // coefficients are read as float4 (M*3 floats = 3M/4 float4 when M in {1,4,9,16}:
+          // M=1 -> 3 floats (not a float4 multiple) so fall back to scalar loads there).
+          float sh[48];
+          const int nfl = a.M * 3;
+          if ((nfl & 3) == 0) {
+#pragma unroll
+            for (int k = 0; k < 12; ++k) {
+              if (k * 4 < nfl) {
+                const float4 v = __ldg(sh4 + k);
+                sh[4 * k + 0] = v.x; sh[4 * k + 1] = v.y; sh[4 * k + 2] = v.z; sh[4 * k + 3] = v.w;
+              }
+            }
+          } else {
+            const float* __restrict__ shf = a.shs + (size_t)idx * a.M * 3;
+#pragma unroll
+            for (int k = 0; k < 48; ++k)
+              if (k < nfl) sh[k] = __ldg(shf + k);
+          }
+#define SHC(k, ch) sh[3 * (k) + (ch)]
+          float res[3];
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) {
+            float v = GCR_SH_C0 * SHC(0, ch);
+            if (a.D > 0) {
+              v = v - GCR_SH_C1 * y * SHC(1, ch) + GCR_SH_C1 * z * SHC(2, ch) -
+                  GCR_SH_C1 * x * SHC(3, ch);
+              if (a.D > 1) {
+                const float xx = x * x, yy = y * y, zz = z * z;
+                const float xy = x * y, yz = y * z, xz = x * z;
+                v = v + GCR_SH_C2[0] * xy * SHC(4, ch) + GCR_SH_C2[1] * yz * SHC(5, ch) +
+                    GCR_SH_C2[2] * (2.0f * zz - xx - yy) * SHC(6, ch) +
+                    GCR_SH_C2[3] * xz * SHC(7, ch) + GCR_SH_C2[4] * (xx - yy) * SHC(8, ch);
+                if (a.D > 2) {
+                  v = v + GCR_SH_C3[0] * y * (3.0f * xx - yy) * SHC(9, ch) +
+                      GCR_SH_C3[1] * xy * z * SHC(10, ch) +
+                      GCR_SH_C3[2] * y * (4.0f * zz - xx - yy) * SHC(11, ch) +
+                      GCR_SH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * SHC(12, ch) +
+                      GCR_SH_C3[4] * x * (4.0f * zz - xx - yy) * SHC(13, ch) +
+                      GCR_SH_C3[5] * z * (xx - yy) * SHC(14, ch) +
+                      GCR_SH_C3[6] * x * (xx - 3.0f * yy) * SHC(15, ch);
+                }
+              }
+            }
+            res[ch] = v + 0.5f;
+          }
+#undef SHC
+          const uint8_t cl = (res[0] < 0 ? 1 : 0) | (res[1] < 0 ? 2 : 0) | (res[2] < 0 ? 4 : 0);
+          a.clamped[idx] = cl;
+          cr = fmaxf(res[0], 0.0f);
+          cg = fmaxf(res[1], 0.0f);
+          cb = fmaxf(res[2], 0.0f);
+        } else {
+          cr = a.colors_precomp[3 * idx + 0];
+          cg = a.colors_precomp[3 * idx + 1];
+          cb = a.colors_precomp[3 * idx + 2];
+        }
+
+        const float opacity = a.opacities[idx];
+        GcrRecord rec;
+        rec.q0 = make_float4(pix_x, pix_y, conic_x, conic_y);
+        rec.q1 = make_float4(conic_z, opacity, cr, cg);
+        // cull threshold 2*ln(255*opacity): a pixel can only reach alpha >= 1/255 when
+        // A dx^2 + 2B dx dy + C dy^2 <= this value (used with a safety margin, blend_*.cu).
+        rec.q2 = make_float4(cb, __uint_as_float((uint32_t)idx), 2.0f * logf(255.0f * opacity), 0.f);
+        a.records[idx] = rec;
+
+        radius_out = (int)my_radius;
+        depth_key = __float_as_uint(vz);
+        // tile count restricted to the tile rows this rank owns (all rows when count == 1)
+        tiles = (rmax.x - rmin.x) *
+                (uint32_t)owned_rows((int)rmin.y, (int)rmax.y, a.shard_rank, a.shard_count);
+      }
+    }
+  }
+  a.radii[idx] = radius_out;
+  a.tiles_touched[idx] = tiles;
+  a.depth_keys[idx] = depth_key;
+}
+
+// mark_visible (rasterizer_impl.cu:52-62): z_view > 0.2
+__global__ void check_frustum_kernel(int P, const float* __restrict__ means3D,
+                                     const float* __restrict__ V, bool* __restrict__ present) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P) return;
+  const float px = means3D[3 * idx], py = means3D[3 * idx + 1], pz = means3D[3 * idx + 2];
+  const float vz = __fadd_rn(xf3(V, 2, px, py, pz), V[14]);
+  present[idx] = vz > 0.2f;
+}
+
+}  // namespace
+
+void gcr_launch_preprocess_fwd(const GcrPreprocessArgs& a, cudaStream_t stream) {
+  if (a.P <= 0) return;
+  const int blocks = (a.P + 255) / 256;
+  if (a.colors_precomp == nullptr)
+    preprocess_fwd_kernel<true><<<blocks, 256, 0, stream>>>(a);
+  else
+    preprocess_fwd_kernel<false><<<blocks, 256, 0, stream>>>(a);
+}
+
+void gcr_launch_check_frustum(int P, const float* means3D, const float* viewmatrix, bool* present,
+                              cudaStream_t stream) {
+  if (P <= 0) return;
+  check_frustum_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, means3D, viewmatrix, present);
+}

@@ -1,0 +1,350 @@
+// preprocess_bwd.cu -- per-Gaussian backward for sm_100a: one fused kernel for what the
+// reference runs as computeCov2DCUDA + preprocessCUDA (DGR/cuda_rasterizer/backward.cu:143-293,
+// 378-425, with the SH backward :20-138 and the scale/rotation backward :297-373).
+//
+// Input: the 48-byte per-Gaussian accumulator filled by blend_bwd (dL/dmean2D, dL/dconic,
+// dL/dopacity, dL/dcolor).  Output: every public gradient tensor, each element written exactly
+// once (zeros for culled Gaussians), so the host does not have to memset (108+12M)*P bytes the
+// way the reference's 9 torch::zeros do.  cov3D is recomputed from scale/rotation instead of
+// being stored by the forward.  Quaternions are NOT normalised and no normalisation Jacobian
+// is applied (backward.cu:301,369-372), as in the reference.
+#include "gcr_common.cuh"
+#include "gcr_kernels.h"
+
+namespace {
+
+// 3x3 matrices use GLM indexing m[col][row]; prod follows glm::operator*(mat3, mat3).
+struct M3 {
+  float m[3][3];
+};
+__forceinline__ __device__ M3 m3_mul(const M3& A, const M3& B) {
+  M3 R;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      R.m[i][j] = A.m[0][j] * B.m[i][0] + A.m[1][j] * B.m[i][1] + A.m[2][j] * B.m[i][2];
+  return R;
+}
+
+template <bool kHasSH>
+__global__ void __launch_bounds__(256)
+preprocess_bwd_kernel(GcrPreprocessBwdArgs a) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.P) return;
+
+  const bool visible = a.radii[idx] > 0;
+  float o_m2x = 0.f, o_m2y = 0.f, o_op = 0.f, o_cr = 0.f, o_cg = 0.f, o_cb = 0.f;
+  float o_ca = 0.f, o_cbb = 0.f, o_cc = 0.f;
+  float dmean[3] = {0.f, 0.f, 0.f};
+  float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float dscale[3] = {0.f, 0.f, 0.f};
+  float drot[4] = {0.f, 0.f, 0.f, 0.f};
+
+  const size_t shbase = (size_t)idx * a.M * 3;
+
+  if (visible) {
+    const float4 g0 = a.grad_acc[idx].g0;
+    const float4 g1 = a.grad_acc[idx].g1;
+    const float g2x = a.grad_acc[idx].g2.x;
+    o_m2x = g0.x; o_m2y = g0.y; o_ca = g0.z; o_cbb = g0.w; o_cc = g1.x; o_op = g1.y;
+    o_cr = g1.z; o_cg = g1.w; o_cb = g2x;
+
+    const float mx = a.means3D[3 * idx], my = a.means3D[3 * idx + 1], mz = a.means3D[3 * idx + 2];
+    const float* __restrict__ V = a.viewmatrix;
+    const float* __restrict__ PM = a.projmatrix;
+
+    // ---- scale / rotation -> M = S R, cov3D (recomputed; forward.cu:110-144) ----
+    float c[6];
+    M3 Rm, Mm;
+    float s[3] = {0.f, 0.f, 0.f};
+    float qr = 0.f, qx = 0.f, qy = 0.f, qz = 0.f;
+    const bool has_scale = a.scales != nullptr;
+    if (has_scale) {
+      s[0] = a.scale_modifier * a.scales[3 * idx + 0];
+      s[1] = a.scale_modifier * a.scales[3 * idx + 1];
+      s[2] = a.scale_modifier * a.scales[3 * idx + 2];
+      const float4 q = reinterpret_cast<const float4*>(a.rotations)[idx];
+      qr = q.x; qx = q.y; qy = q.z; qz = q.w;
+      Rm.m[0][0] = 1.f - 2.f * (qy * qy + qz * qz);
+      Rm.m[0][1] = 2.f * (qx * qy - qr * qz);
+      Rm.m[0][2] = 2.f * (qx * qz + qr * qy);
+      Rm.m[1][0] = 2.f * (qx * qy + qr * qz);
+      Rm.m[1][1] = 1.f - 2.f * (qx * qx + qz * qz);
+      Rm.m[1][2] = 2.f * (qy * qz - qr * qx);
+      Rm.m[2][0] = 2.f * (qx * qz - qr * qy);
+      Rm.m[2][1] = 2.f * (qy * qz + qr * qx);
+      Rm.m[2][2] = 1.f - 2.f * (qx * qx + qy * qy);
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) Mm.m[i][j] = s[j] * Rm.m[i][j];
+    }
+    if (a.cov3D_precomp != nullptr) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) c[k] = a.cov3D_precomp[6 * (size_t)idx + k];
+    } else {
+      // Sigma[i][j] = sum_k M[j][k] M[i][k]
+      c[0] = Mm.m[0][0] * Mm.m[0][0] + Mm.m[0][1] * Mm.m[0][1] + Mm.m[0][2] * Mm.m[0][2];
+      c[1] = Mm.m[1][0] * Mm.m[0][0] + Mm.m[1][1] * Mm.m[0][1] + Mm.m[1][2] * Mm.m[0][2];
+      c[2] = Mm.m[2][0] * Mm.m[0][0] + Mm.m[2][1] * Mm.m[0][1] + Mm.m[2][2] * Mm.m[0][2];
+      c[3] = Mm.m[1][0] * Mm.m[1][0] + Mm.m[1][1] * Mm.m[1][1] + Mm.m[1][2] * Mm.m[1][2];
+      c[4] = Mm.m[2][0] * Mm.m[1][0] + Mm.m[2][1] * Mm.m[1][1] + Mm.m[2][2] * Mm.m[1][2];
+      c[5] = Mm.m[2][0] * Mm.m[2][0] + Mm.m[2][1] * Mm.m[2][1] + Mm.m[2][2] * Mm.m[2][2];
+    }
+
+    // ---- 2D covariance backward (backward.cu:143-293) ----
+    float tx = V[0] * mx + V[4] * my + V[8] * mz + V[12];
+    float ty = V[1] * mx + V[5] * my + V[9] * mz + V[13];
+    const float tz = V[2] * mx + V[6] * my + V[10] * mz + V[14];
+    const float limx = 1.3f * a.tan_fovx, limy = 1.3f * a.tan_fovy;
+    const float txtz = tx / tz, tytz = ty / tz;
+    tx = fminf(limx, fmaxf(-limx, txtz)) * tz;
+    ty = fminf(limy, fmaxf(-limy, tytz)) * tz;
+    const float x_grad_mul = (txtz < -limx || txtz > limx) ? 0.f : 1.f;
+    const float y_grad_mul = (tytz < -limy || tytz > limy) ? 0.f : 1.f;
+
+    M3 J, Wm, Vrk;
+    J.m[0][0] = a.focal_x / tz; J.m[0][1] = 0.f; J.m[0][2] = -(a.focal_x * tx) / (tz * tz);
+    J.m[1][0] = 0.f; J.m[1][1] = a.focal_y / tz; J.m[1][2] = -(a.focal_y * ty) / (tz * tz);
+    J.m[2][0] = 0.f; J.m[2][1] = 0.f; J.m[2][2] = 0.f;
+    Wm.m[0][0] = V[0]; Wm.m[0][1] = V[4]; Wm.m[0][2] = V[8];
+    Wm.m[1][0] = V[1]; Wm.m[1][1] = V[5]; Wm.m[1][2] = V[9];
+    Wm.m[2][0] = V[2]; Wm.m[2][1] = V[6]; Wm.m[2][2] = V[10];
+    Vrk.m[0][0] = c[0]; Vrk.m[0][1] = c[1]; Vrk.m[0][2] = c[2];
+    Vrk.m[1][0] = c[1]; Vrk.m[1][1] = c[3]; Vrk.m[1][2] = c[4];
+    Vrk.m[2][0] = c[2]; Vrk.m[2][1] = c[4]; Vrk.m[2][2] = c[5];
+    const M3 Tm = m3_mul(Wm, J);
+    // cov2D = T^T Vrk^T T ; only the upper-left 2x2 is needed
+    M3 Tt, X;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) Tt.m[i][j] = Tm.m[j][i];
+    X = m3_mul(m3_mul(Tt, Vrk), Tm);  // Vrk symmetric
+    const float ca = X.m[0][0] + 0.3f;
+    const float cb = X.m[0][1];
+    const float cc = X.m[1][1] + 0.3f;
+    const float denom = ca * cc - cb * cb;
+    float dL_da = 0.f, dL_db = 0.f, dL_dc = 0.f;
+    const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+    const float dcx = o_ca, dcy = o_cbb, dcz = o_cc;  // dL/dconic (x, y, w)
+    if (denom2inv != 0.f) {
+      dL_da = denom2inv * (-cc * cc * dcx + 2.f * cb * cc * dcy + (denom - ca * cc) * dcz);
+      dL_dc = denom2inv * (-ca * ca * dcz + 2.f * ca * cb * dcy + (denom - ca * cc) * dcx);
+      dL_db = denom2inv * 2.f * (cb * cc * dcx - (denom + 2.f * cb * cb) * dcy + ca * cb * dcz);
+      const float T00 = Tm.m[0][0], T01 = Tm.m[0][1], T02 = Tm.m[0][2];
+      const float T10 = Tm.m[1][0], T11 = Tm.m[1][1], T12 = Tm.m[1][2];
+      dcov[0] = T00 * T00 * dL_da + T00 * T10 * dL_db + T10 * T10 * dL_dc;
+      dcov[3] = T01 * T01 * dL_da + T01 * T11 * dL_db + T11 * T11 * dL_dc;
+      dcov[5] = T02 * T02 * dL_da + T02 * T12 * dL_db + T12 * T12 * dL_dc;
+      dcov[1] = 2.f * T00 * T01 * dL_da + (T00 * T11 + T01 * T10) * dL_db + 2.f * T10 * T11 * dL_dc;
+      dcov[2] = 2.f * T00 * T02 * dL_da + (T00 * T12 + T02 * T10) * dL_db + 2.f * T10 * T12 * dL_dc;
+      dcov[4] = 2.f * T02 * T01 * dL_da + (T01 * T12 + T02 * T11) * dL_db + 2.f * T11 * T12 * dL_dc;
+    }
+    {
+      const float T00 = Tm.m[0][0], T01 = Tm.m[0][1], T02 = Tm.m[0][2];
+      const float T10 = Tm.m[1][0], T11 = Tm.m[1][1], T12 = Tm.m[1][2];
+      // row-vectors u_k = T[0][:] . Vrk[k][:], w_k = T[1][:] . Vrk[k][:]
+      float u[3], w[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        u[k] = T00 * Vrk.m[k][0] + T01 * Vrk.m[k][1] + T02 * Vrk.m[k][2];
+        w[k] = T10 * Vrk.m[k][0] + T11 * Vrk.m[k][1] + T12 * Vrk.m[k][2];
+      }
+      const float dT00 = 2.f * u[0] * dL_da + w[0] * dL_db;
+      const float dT01 = 2.f * u[1] * dL_da + w[1] * dL_db;
+      const float dT02 = 2.f * u[2] * dL_da + w[2] * dL_db;
+      const float dT10 = 2.f * w[0] * dL_dc + u[0] * dL_db;
+      const float dT11 = 2.f * w[1] * dL_dc + u[1] * dL_db;
+      const float dT12 = 2.f * w[2] * dL_dc + u[2] * dL_db;
+      const float dJ00 = Wm.m[0][0] * dT00 + Wm.m[0][1] * dT01 + Wm.m[0][2] * dT02;
+      const float dJ02 = Wm.m[2][0] * dT00 + Wm.m[2][1] * dT01 + Wm.m[2][2] * dT02;
+      const float dJ11 = Wm.m[1][0] * dT10 + Wm.m[1][1] * dT11 + Wm.m[1][2] * dT12;
+      const float dJ12 = Wm.m[2][0] * dT10 + Wm.m[2][1] * dT11 + Wm.m[2][2] * dT12;
+      const float itz = 1.f / tz;
+      const float itz2 = itz * itz;
+      const float itz3 = itz2 * itz;
+      const float dtx = x_grad_mul * -a.focal_x * itz2 * dJ02;
+      const float dty = y_grad_mul * -a.focal_y * itz2 * dJ12;
+      const float dtz = -a.focal_x * itz2 * dJ00 - a.focal_y * itz2 * dJ11 +
+                        (2.f * a.focal_x * tx) * itz3 * dJ02 + (2.f * a.focal_y * ty) * itz3 * dJ12;
+      // dL/dmean (covariance path) = W^T-transposed transform (transformVec4x3Transpose)
+      dmean[0] = V[0] * dtx + V[1] * dty + V[2] * dtz;
+      dmean[1] = V[4] * dtx + V[5] * dty + V[6] * dtz;
+      dmean[2] = V[8] * dtx + V[9] * dty + V[10] * dtz;
+    }
+
+    // ---- screen-space mean gradient -> 3D mean (backward.cu:389-413) ----
+    {
+      const float hw = PM[3] * mx + PM[7] * my + PM[11] * mz + PM[15];
+      const float m_w = 1.0f / (hw + 0.0000001f);
+      const float mul1 = (PM[0] * mx + PM[4] * my + PM[8] * mz + PM[12]) * m_w * m_w;
+      const float mul2 = (PM[1] * mx + PM[5] * my + PM[9] * mz + PM[13]) * m_w * m_w;
+      dmean[0] += (PM[0] * m_w - PM[3] * mul1) * o_m2x + (PM[1] * m_w - PM[3] * mul2) * o_m2y;
+      dmean[1] += (PM[4] * m_w - PM[7] * mul1) * o_m2x + (PM[5] * m_w - PM[7] * mul2) * o_m2y;
+      dmean[2] += (PM[8] * m_w - PM[11] * mul1) * o_m2x + (PM[9] * m_w - PM[11] * mul2) * o_m2y;
+    }
+
+    // ---- SH backward (backward.cu:20-138) ----
+    if (kHasSH) {
+      const float dox = mx - a.campos[0], doy = my - a.campos[1], doz = mz - a.campos[2];
+      const float len = sqrtf(dox * dox + doy * doy + doz * doz);
+      const float x = dox / len, y = doy / len, z = doz / len;
+      const uint8_t cl = a.clamped[idx];
+      float dRGB[3] = {(cl & 1) ? 0.f : o_cr, (cl & 2) ? 0.f : o_cg, (cl & 4) ? 0.f : o_cb};
+      const float* __restrict__ sh = a.shs + shbase;
+      float* __restrict__ dsh = a.dL_dsh + shbase;
+      float dRGBdx[3] = {0, 0, 0}, dRGBdy[3] = {0, 0, 0}, dRGBdz[3] = {0, 0, 0};
+#define SH(k, ch) __ldg(sh + 3 * (k) + (ch))
+#define DSH(k, v)                                  \
+  {                                                \
+    dsh[3 * (k) + 0] = (v) * dRGB[0];              \
+    dsh[3 * (k) + 1] = (v) * dRGB[1];              \
+    dsh[3 * (k) + 2] = (v) * dRGB[2];              \
+  }
+      DSH(0, GCR_SH_C0);
+      if (a.D > 0) {
+        DSH(1, -GCR_SH_C1 * y);
+        DSH(2, GCR_SH_C1 * z);
+        DSH(3, -GCR_SH_C1 * x);
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          dRGBdx[ch] = -GCR_SH_C1 * SH(3, ch);
+          dRGBdy[ch] = -GCR_SH_C1 * SH(1, ch);
+          dRGBdz[ch] = GCR_SH_C1 * SH(2, ch);
+        }
+        if (a.D > 1) {
+          const float xx = x * x, yy = y * y, zz = z * z;
+          const float xy = x * y, yz = y * z, xz = x * z;
+          DSH(4, GCR_SH_C2[0] * xy);
+          DSH(5, GCR_SH_C2[1] * yz);
+          DSH(6, GCR_SH_C2[2] * (2.f * zz - xx - yy));
+          DSH(7, GCR_SH_C2[3] * xz);
+          DSH(8, GCR_SH_C2[4] * (xx - yy));
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) {
+            dRGBdx[ch] += GCR_SH_C2[0] * y * SH(4, ch) + GCR_SH_C2[2] * 2.f * -x * SH(6, ch) +
+                          GCR_SH_C2[3] * z * SH(7, ch) + GCR_SH_C2[4] * 2.f * x * SH(8, ch);
+            dRGBdy[ch] += GCR_SH_C2[0] * x * SH(4, ch) + GCR_SH_C2[1] * z * SH(5, ch) +
+                          GCR_SH_C2[2] * 2.f * -y * SH(6, ch) + GCR_SH_C2[4] * 2.f * -y * SH(8, ch);
+            dRGBdz[ch] += GCR_SH_C2[1] * y * SH(5, ch) + GCR_SH_C2[2] * 2.f * 2.f * z * SH(6, ch) +
+                          GCR_SH_C2[3] * x * SH(7, ch);
+          }
+          if (a.D > 2) {
+            DSH(9, GCR_SH_C3[0] * y * (3.f * xx - yy));
+            DSH(10, GCR_SH_C3[1] * xy * z);
+            DSH(11, GCR_SH_C3[2] * y * (4.f * zz - xx - yy));
+            DSH(12, GCR_SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy));
+            DSH(13, GCR_SH_C3[4] * x * (4.f * zz - xx - yy));
+            DSH(14, GCR_SH_C3[5] * z * (xx - yy));
+            DSH(15, GCR_SH_C3[6] * x * (xx - 3.f * yy));
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+              dRGBdx[ch] += GCR_SH_C3[0] * SH(9, ch) * 3.f * 2.f * xy +
+                            GCR_SH_C3[1] * SH(10, ch) * yz + GCR_SH_C3[2] * SH(11, ch) * -2.f * xy +
+                            GCR_SH_C3[3] * SH(12, ch) * -3.f * 2.f * xz +
+                            GCR_SH_C3[4] * SH(13, ch) * (-3.f * xx + 4.f * zz - yy) +
+                            GCR_SH_C3[5] * SH(14, ch) * 2.f * xz +
+                            GCR_SH_C3[6] * SH(15, ch) * 3.f * (xx - yy);
+              dRGBdy[ch] += GCR_SH_C3[0] * SH(9, ch) * 3.f * (xx - yy) +
+                            GCR_SH_C3[1] * SH(10, ch) * xz +
+                            GCR_SH_C3[2] * SH(11, ch) * (-3.f * yy + 4.f * zz - xx) +
+                            GCR_SH_C3[3] * SH(12, ch) * -3.f * 2.f * yz +
+                            GCR_SH_C3[4] * SH(13, ch) * -2.f * xy +
+                            GCR_SH_C3[5] * SH(14, ch) * -2.f * yz +
+                            GCR_SH_C3[6] * SH(15, ch) * -3.f * 2.f * xy;
+              dRGBdz[ch] += GCR_SH_C3[1] * SH(10, ch) * xy +
+                            GCR_SH_C3[2] * SH(11, ch) * 4.f * 2.f * yz +
+                            GCR_SH_C3[3] * SH(12, ch) * 3.f * (2.f * zz - xx - yy) +
+                            GCR_SH_C3[4] * SH(13, ch) * 4.f * 2.f * xz +
+                            GCR_SH_C3[5] * SH(14, ch) * (xx - yy);
+            }
+          }
+        }
+      }
+      // coefficients above the active degree receive zero gradient
+      {
+        const int used = (a.D + 1) * (a.D + 1);
+        for (int k = used; k < a.M; ++k) {
+          dsh[3 * k + 0] = 0.f; dsh[3 * k + 1] = 0.f; dsh[3 * k + 2] = 0.f;
+        }
+      }
+#undef SH
+#undef DSH
+      const float ddx = dRGBdx[0] * dRGB[0] + dRGBdx[1] * dRGB[1] + dRGBdx[2] * dRGB[2];
+      const float ddy = dRGBdy[0] * dRGB[0] + dRGBdy[1] * dRGB[1] + dRGBdy[2] * dRGB[2];
+      const float ddz = dRGBdz[0] * dRGB[0] + dRGBdz[1] * dRGB[1] + dRGBdz[2] * dRGB[2];
+      // normalisation Jacobian (dnormvdv, auxiliary.h:95-112)
+      const float sum2 = dox * dox + doy * doy + doz * doz;
+      const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
+      dmean[0] += ((sum2 - dox * dox) * ddx - doy * dox * ddy - doz * dox * ddz) * invsum32;
+      dmean[1] += (-dox * doy * ddx + (sum2 - doy * doy) * ddy - doz * doy * ddz) * invsum32;
+      dmean[2] += (-dox * doz * ddx - doy * doz * ddy + (sum2 - doz * doz) * ddz) * invsum32;
+    }
+
+    // ---- scale / rotation backward (backward.cu:297-373) ----
+    if (has_scale) {
+      M3 dS;
+      dS.m[0][0] = dcov[0]; dS.m[0][1] = 0.5f * dcov[1]; dS.m[0][2] = 0.5f * dcov[2];
+      dS.m[1][0] = 0.5f * dcov[1]; dS.m[1][1] = dcov[3]; dS.m[1][2] = 0.5f * dcov[4];
+      dS.m[2][0] = 0.5f * dcov[2]; dS.m[2][1] = 0.5f * dcov[4]; dS.m[2][2] = dcov[5];
+      M3 dM = m3_mul(Mm, dS);
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) dM.m[i][j] *= 2.0f;
+      // dL_dMt[a][b] = dM[b][a];  Rt[a][b] = R[b][a]
+      dscale[0] = Rm.m[0][0] * dM.m[0][0] + Rm.m[1][0] * dM.m[1][0] + Rm.m[2][0] * dM.m[2][0];
+      dscale[1] = Rm.m[0][1] * dM.m[0][1] + Rm.m[1][1] * dM.m[1][1] + Rm.m[2][1] * dM.m[2][1];
+      dscale[2] = Rm.m[0][2] * dM.m[0][2] + Rm.m[1][2] * dM.m[1][2] + Rm.m[2][2] * dM.m[2][2];
+      float t[3][3];  // t[a][b] = dL_dMt[a][b] * s_a
+#pragma unroll
+      for (int p = 0; p < 3; ++p)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) t[p][q] = dM.m[q][p] * s[p];
+      drot[0] = 2.f * qz * (t[0][1] - t[1][0]) + 2.f * qy * (t[2][0] - t[0][2]) +
+                2.f * qx * (t[1][2] - t[2][1]);
+      drot[1] = 2.f * qy * (t[1][0] + t[0][1]) + 2.f * qz * (t[2][0] + t[0][2]) +
+                2.f * qr * (t[1][2] - t[2][1]) - 4.f * qx * (t[2][2] + t[1][1]);
+      drot[2] = 2.f * qx * (t[1][0] + t[0][1]) + 2.f * qr * (t[2][0] - t[0][2]) +
+                2.f * qz * (t[1][2] + t[2][1]) - 4.f * qy * (t[2][2] + t[0][0]);
+      drot[3] = 2.f * qr * (t[0][1] - t[1][0]) + 2.f * qx * (t[2][0] + t[0][2]) +
+                2.f * qy * (t[1][2] + t[2][1]) - 4.f * qz * (t[1][1] + t[0][0]);
+    }
+  } else if (kHasSH) {
+    float* __restrict__ dsh = a.dL_dsh + shbase;
+    for (int k = 0; k < a.M * 3; ++k) dsh[k] = 0.f;
+  }
+
+  a.dL_dmean2D[3 * idx + 0] = o_m2x;
+  a.dL_dmean2D[3 * idx + 1] = o_m2y;
+  a.dL_dmean2D[3 * idx + 2] = 0.f;
+  if (a.dL_dconic != nullptr)
+    reinterpret_cast<float4*>(a.dL_dconic)[idx] = make_float4(o_ca, o_cbb, 0.f, o_cc);
+  a.dL_dopacity[idx] = o_op;
+  a.dL_dcolor[3 * idx + 0] = o_cr;
+  a.dL_dcolor[3 * idx + 1] = o_cg;
+  a.dL_dcolor[3 * idx + 2] = o_cb;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) a.dL_dmean3D[3 * idx + k] = dmean[k];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) a.dL_dcov3D[6 * (size_t)idx + k] = dcov[k];
+  if (a.dL_dscale != nullptr) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) a.dL_dscale[3 * idx + k] = dscale[k];
+  }
+  if (a.dL_drot != nullptr)
+    reinterpret_cast<float4*>(a.dL_drot)[idx] = make_float4(drot[0], drot[1], drot[2], drot[3]);
+}
+
+}  // namespace
+
+void gcr_launch_preprocess_bwd(const GcrPreprocessBwdArgs& a, cudaStream_t stream) {
+  if (a.P <= 0) return;
+  const int blocks = (a.P + 255) / 256;
+  if (a.shs != nullptr && a.M > 0)
+    preprocess_bwd_kernel<true><<<blocks, 256, 0, stream>>>(a);
+  else
+    preprocess_bwd_kernel<false><<<blocks, 256, 0, stream>>>(a);
+}

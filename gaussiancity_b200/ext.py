@@ -1,0 +1,175 @@
+"""Seam A: the three native entry points of the reference's pybind module
+`diff_gaussian_rasterization_ext` (DGR/bindings.cpp:15-18), with the same positional signatures
+and return tuples as RasterizeGaussiansCUDA / RasterizeGaussiansBackwardCUDA / markVisible
+(DGR/rasterize_points.cu:35-173), implemented over the C ABI (include/gcr_rasterizer.h).
+
+Host-side responsibilities kept from the reference boundary: output allocation, the three
+resizable byte buffers (here: torch uint8 tensors handed out through the allocator callback),
+`.contiguous()` on every input, empty tensor == absent optional, P == 0 short-circuit.
+Differences: kernels run on torch's CURRENT stream (the reference uses the legacy default
+stream); gradient tensors are torch.empty (the kernels write every element).
+"""
+import ctypes
+
+import torch
+
+from . import _cabi
+
+NUM_CHANNELS = 3  # DGR/cuda_rasterizer/config.h:15
+
+
+def _ptr(t):
+    """Device pointer or NULL for an empty tensor (reference: empty tensor -> nullptr)."""
+    if t is None or t.numel() == 0:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _prep(t, name, device, align=4):
+    if t is None:
+        return None
+    if t.numel() == 0:
+        return t
+    if t.device != device:
+        raise RuntimeError(f"{name} must be on {device}, got {t.device}")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name} must be float32, got {t.dtype}")
+    t = t.contiguous()
+    if t.data_ptr() % align != 0:
+        t = t.clone()
+    return t
+
+
+def _stream_ptr(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class _Allocator:
+    """Resizable byte buffer handed to the library (resizeFunctional, rasterize_points.cu:27-33)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.tensor = torch.empty(0, dtype=torch.uint8, device=device)
+        self.cb = _cabi.ALLOC_FN(self._alloc)
+
+    def _alloc(self, _ctx, nbytes):
+        try:
+            self.tensor = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+            return self.tensor.data_ptr()
+        except Exception:  # surfaces as "allocation failed" from the library
+            return 0
+
+
+def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier,
+                        cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height,
+                        image_width, sh, degree, campos, prefiltered, debug,
+                        shard_rank=0, shard_count=1):
+    """-> (num_rendered, color[3,H,W], radii[P] int32, geomBuffer, binningBuffer, imgBuffer)"""
+    if means3D.dim() != 2 or means3D.size(1) != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")
+    if not means3D.is_cuda:
+        raise RuntimeError("means3D must be a CUDA tensor (there is no CPU path)")
+    lib = _cabi.lib()
+    device = means3D.device
+    P, H, W = int(means3D.size(0)), int(image_height), int(image_width)
+
+    with torch.cuda.device(device):
+        out_color = torch.zeros((NUM_CHANNELS, H, W), dtype=torch.float32, device=device)
+        radii = torch.zeros((P,), dtype=torch.int32, device=device)
+        geom, binning, img = _Allocator(device), _Allocator(device), _Allocator(device)
+        rendered = 0
+        if P != 0:
+            M = int(sh.size(1)) if sh.numel() != 0 else 0
+            background = _prep(background, "background", device)
+            means3D = _prep(means3D, "means3D", device)
+            colors = _prep(colors, "colors_precomp", device)
+            opacity = _prep(opacity, "opacity", device)
+            scales = _prep(scales, "scales", device)
+            rotations = _prep(rotations, "rotations", device, align=16)
+            cov3D_precomp = _prep(cov3D_precomp, "cov3D_precomp", device)
+            viewmatrix = _prep(viewmatrix, "viewmatrix", device)
+            projmatrix = _prep(projmatrix, "projmatrix", device)
+            sh = _prep(sh, "sh", device, align=16)
+            campos = _prep(campos, "campos", device)
+            rc = lib.gcr_rasterizer_forward(
+                geom.cb, None, binning.cb, None, img.cb, None,
+                P, int(degree), M, _ptr(background), W, H,
+                _ptr(means3D), _ptr(sh), _ptr(colors), _ptr(opacity), _ptr(scales),
+                float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp), _ptr(viewmatrix),
+                _ptr(projmatrix), _ptr(campos), float(tan_fovx), float(tan_fovy),
+                int(bool(prefiltered)), _ptr(out_color), _ptr(radii), int(bool(debug)),
+                int(shard_rank), int(shard_count), _stream_ptr(device))
+            rendered = _cabi.check(rc, "rasterize_gaussians")
+    return rendered, out_color, radii, geom.tensor, binning.tensor, img.tensor
+
+
+def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations,
+                                 scale_modifier, cov3D_precomp, viewmatrix, projmatrix, tan_fovx,
+                                 tan_fovy, dL_dout_color, sh, degree, campos, geomBuffer, R,
+                                 binningBuffer, imageBuffer, debug, shard_rank=0, shard_count=1):
+    """-> (dL_dmeans2D[P,3], dL_dcolors[P,3], dL_dopacity[P,1], dL_dmeans3D[P,3],
+           dL_dcov3D[P,6], dL_dsh[P,M,3], dL_dscales[P,3], dL_drotations[P,4])"""
+    lib = _cabi.lib()
+    device = means3D.device
+    P = int(means3D.size(0))
+    H, W = int(dL_dout_color.size(1)), int(dL_dout_color.size(2))
+    M = int(sh.size(1)) if sh.numel() != 0 else 0
+    opts = dict(dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        alloc = torch.empty if P != 0 else torch.zeros
+        dL_dmeans3D = alloc((P, 3), **opts)
+        dL_dmeans2D = alloc((P, 3), **opts)
+        dL_dcolors = alloc((P, NUM_CHANNELS), **opts)
+        dL_dopacity = alloc((P, 1), **opts)
+        dL_dcov3D = alloc((P, 6), **opts)
+        dL_dsh = alloc((P, M, 3), **opts)
+        dL_dscales = alloc((P, 3), **opts)
+        dL_drotations = alloc((P, 4), **opts)
+        if P != 0:
+            background = _prep(background, "background", device)
+            means3D = _prep(means3D, "means3D", device)
+            colors = _prep(colors, "colors_precomp", device)
+            scales = _prep(scales, "scales", device)
+            rotations = _prep(rotations, "rotations", device, align=16)
+            cov3D_precomp = _prep(cov3D_precomp, "cov3D_precomp", device)
+            viewmatrix = _prep(viewmatrix, "viewmatrix", device)
+            projmatrix = _prep(projmatrix, "projmatrix", device)
+            sh = _prep(sh, "sh", device, align=16)
+            campos = _prep(campos, "campos", device)
+            dL_dout_color = _prep(dL_dout_color, "dL_dout_color", device)
+            radii = radii.contiguous()
+            rc = lib.gcr_rasterizer_backward(
+                P, int(degree), M, int(R), _ptr(background), W, H, _ptr(means3D), _ptr(sh),
+                _ptr(colors), _ptr(scales), float(scale_modifier), _ptr(rotations),
+                _ptr(cov3D_precomp), _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos),
+                float(tan_fovx), float(tan_fovy), _ptr(radii),
+                ctypes.c_void_p(geomBuffer.data_ptr()),
+                ctypes.c_void_p(binningBuffer.data_ptr()) if binningBuffer.numel() else None,
+                ctypes.c_void_p(imageBuffer.data_ptr()),
+                _ptr(dL_dout_color), _ptr(dL_dmeans2D), None, _ptr(dL_dopacity),
+                _ptr(dL_dcolors), _ptr(dL_dmeans3D), _ptr(dL_dcov3D), _ptr(dL_dsh),
+                _ptr(dL_dscales), _ptr(dL_drotations), int(bool(debug)),
+                int(shard_rank), int(shard_count), _stream_ptr(device))
+            _cabi.check(rc, "rasterize_gaussians_backward")
+    return (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales,
+            dL_drotations)
+
+
+def mark_visible(means3D, viewmatrix, projmatrix):
+    """-> bool[P]: view-space depth > 0.2 (checkFrustum, rasterizer_impl.cu:52-62)"""
+    lib = _cabi.lib()
+    device = means3D.device
+    if not means3D.is_cuda:
+        raise RuntimeError("means3D must be a CUDA tensor (there is no CPU path)")
+    P = int(means3D.size(0))
+    with torch.cuda.device(device):
+        present = torch.zeros((P,), dtype=torch.bool, device=device)
+        if P != 0:
+            means3D = _prep(means3D, "means3D", device)
+            viewmatrix = _prep(viewmatrix, "viewmatrix", device)
+            projmatrix = _prep(projmatrix, "projmatrix", device)
+            rc = lib.gcr_rasterizer_mark_visible(P, _ptr(means3D), _ptr(viewmatrix),
+                                                 _ptr(projmatrix), _ptr(present),
+                                                 _stream_ptr(device))
+            _cabi.check(rc, "mark_visible")
+    return present

@@ -1,0 +1,95 @@
+#!/usr/bin/env python
+"""Build the UNMODIFIED reference extension into oracle/_ref/ (test infrastructure).
+
+Compiles the five reference source files where they lie under /root/reference
+(extensions/diff_gaussian_rasterization/{cuda_rasterizer/{forward,backward,
+rasterizer_impl}.cu, rasterize_points.cu, bindings.cpp}) for sm_100a with the
+reference's own flags (setup.py:20-37: only `-I third_party/glm`; no
+-use_fast_math, default -fmad=true).  The single deviation is `-include cstdint`
+(rasterizer_impl.h:24,40-59 uses std::uintptr_t/uint32_t without including
+<cstdint>, which gcc 13 rejects).  No reference source is copied into this repo:
+objects go to a temp dir, only the linked .so lands in oracle/_ref/ (git-ignored,
+but shipped to the GPU box by gpurun).
+
+The result, oracle/_ref/diff_gaussian_rasterization_ext*.so, is the parity pin
+for the `-m gpu` tests and the `bench.py --impl reference` arm.  It is never
+imported by the product package.
+"""
+import os
+import subprocess
+import sys
+import sysconfig
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT_DIR = os.path.join(HERE, "_ref")
+REF = os.environ.get("GCR_REFERENCE_ROOT", "/root/reference")
+DGR = os.path.join(REF, "extensions", "diff_gaussian_rasterization")
+MODNAME = "diff_gaussian_rasterization_ext"
+
+
+def so_path():
+    return os.path.join(OUT_DIR, MODNAME + sysconfig.get_config_var("EXT_SUFFIX"))
+
+
+def build(force=False, verbose=False):
+    """Returns the .so path, or None when /root/reference is absent (GPU box)."""
+    out = so_path()
+    if not os.path.isdir(DGR):
+        return out if os.path.exists(out) else None
+    srcs = [
+        os.path.join(DGR, "cuda_rasterizer", "rasterizer_impl.cu"),
+        os.path.join(DGR, "cuda_rasterizer", "forward.cu"),
+        os.path.join(DGR, "cuda_rasterizer", "backward.cu"),
+        os.path.join(DGR, "rasterize_points.cu"),
+        os.path.join(DGR, "bindings.cpp"),
+    ]
+    if not force and os.path.exists(out):
+        newest = max(os.path.getmtime(s) for s in srcs + [__file__])
+        if os.path.getmtime(out) >= newest:
+            return out
+    import torch  # noqa: F401  (only for include/lib discovery)
+    from torch.utils import cpp_extension as ce
+
+    os.makedirs(OUT_DIR, exist_ok=True)
+    incs = ce.include_paths() + [sysconfig.get_paths()["include"],
+                                 os.path.join(DGR, "third_party", "glm"),
+                                 os.path.join(DGR, "cuda_rasterizer")]
+    inc_flags = [f"-I{p}" for p in incs]
+    common = ["-O3", "-std=c++17", "-include", "cstdint",
+              f"-DTORCH_EXTENSION_NAME={MODNAME}", "-DTORCH_API_INCLUDE_EXTENSION_H",
+              "-D_GLIBCXX_USE_CXX11_ABI=1"]
+    tmp = tempfile.mkdtemp(prefix="gcr_refbuild_")
+    objs = []
+    procs = []
+    for s in srcs:
+        o = os.path.join(tmp, os.path.basename(s) + ".o")
+        objs.append(o)
+        if s.endswith(".cu"):
+            cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+                   "-Xcompiler", "-fPIC", "-w"] + common + inc_flags + ["-c", s, "-o", o]
+        else:
+            cmd = ["g++", "-fPIC", "-w"] + common + inc_flags + ["-c", s, "-o", o]
+        if verbose:
+            print(" ".join(cmd))
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
+    for cmd, p in procs:
+        log, _ = p.communicate()
+        if p.returncode != 0:
+            sys.stderr.write(log.decode())
+            raise RuntimeError("reference build failed: " + " ".join(cmd))
+    libdirs = ce.library_paths()
+    link = ["g++", "-shared", "-o", out] + objs
+    for d in libdirs:
+        link += [f"-L{d}", f"-Wl,-rpath,{d}"]
+    link += ["-L/usr/local/cuda/lib64", "-lc10", "-ltorch_cpu", "-ltorch", "-ltorch_python",
+             "-lc10_cuda", "-ltorch_cuda", "-lcudart"]
+    if verbose:
+        print(" ".join(link))
+    subprocess.check_call(link)
+    return out
+
+
+if __name__ == "__main__":
+    p = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print(p if p else "reference sources absent and no prebuilt oracle/_ref")
