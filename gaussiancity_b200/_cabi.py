@@ -22,6 +22,11 @@ EXPORTED_SYMBOLS = (
     "gcr_rasterizer_backward_geometry",
     "gcr_rasterizer_mark_visible",
     "gcr_debug_offset",
+    "gcr_debug_set_cov3d_out",
+    "gcr_profile_enable",
+    "gcr_profile_stage_count",
+    "gcr_profile_stage_name",
+    "gcr_profile_stage_ms",
 )
 
 # enum values of gcr_debug_offset (include/gcr_rasterizer.h)
@@ -58,11 +63,21 @@ def _declare(l):
     l.gcr_rasterizer_backward_geometry.restype = c_int
     l.gcr_rasterizer_backward_geometry.argtypes = (
         [c_int] * 3 + [c_void_p] * 3 + [c_float] + [c_void_p] * 5 + [c_int, c_int, c_float, c_float] +
-        [c_void_p] * 12 + [c_int, c_void_p])
+        [c_void_p] * 12 + [c_int, c_int, c_int, c_void_p])
     l.gcr_rasterizer_mark_visible.restype = c_int
     l.gcr_rasterizer_mark_visible.argtypes = [c_int] + [c_void_p] * 5
     l.gcr_debug_offset.restype = c_size_t
     l.gcr_debug_offset.argtypes = [c_int] * 5
+    l.gcr_debug_set_cov3d_out.restype = None
+    l.gcr_debug_set_cov3d_out.argtypes = [c_void_p]
+    l.gcr_profile_enable.restype = None
+    l.gcr_profile_enable.argtypes = [c_int]
+    l.gcr_profile_stage_count.restype = c_int
+    l.gcr_profile_stage_count.argtypes = []
+    l.gcr_profile_stage_name.restype = ctypes.c_char_p
+    l.gcr_profile_stage_name.argtypes = [c_int]
+    l.gcr_profile_stage_ms.restype = c_float
+    l.gcr_profile_stage_ms.argtypes = [c_int]
 
 
 def lib():
@@ -95,3 +110,18 @@ def check(rc, what):
     if rc < 0:
         raise RuntimeError(f"{what}: {last_error()}")
     return rc
+
+
+def profile_enable(on=True):
+    lib().gcr_profile_enable(1 if on else 0)
+
+
+def profile_read():
+    """{stage name: device ms} of the most recent profiled call (call after synchronising)."""
+    l = lib()
+    out = {}
+    for i in range(l.gcr_profile_stage_count()):
+        ms = l.gcr_profile_stage_ms(i)
+        if ms >= 0:
+            out[l.gcr_profile_stage_name(i).decode()] = float(ms)
+    return out

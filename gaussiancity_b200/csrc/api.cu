@@ -20,6 +20,45 @@
 namespace {
 
 thread_local std::string g_last_error;
+thread_local float* g_dbg_cov3d = nullptr;  // test hook: next forward also writes cov3D here
+
+// ---- optional per-stage timing with CUDA events recorded on the caller's stream (no host
+// sync is added; bench.py reads the elapsed times after it has synchronised) -----------------
+enum Stage {
+  ST_PREPROCESS = 0, ST_DEPTH_SORT, ST_SCAN, ST_EMIT, ST_TILE_SORT, ST_RANGES_GATHER, ST_BLEND_FWD,
+  ST_BWD_ZERO, ST_BLEND_BWD, ST_GEOM_BWD, ST_COUNT
+};
+const char* const kStageNames[ST_COUNT] = {"preprocess_fwd", "depth_sort", "scan", "emit_pairs",
+                                           "tile_sort", "ranges_gather", "blend_fwd", "bwd_zero",
+                                           "blend_bwd", "geometry_bwd"};
+constexpr int kProfSlots = 64;  // ring of profiled forward(+backward) calls
+struct Profiler {
+  bool enabled = false;
+  bool created = false;
+  int slot = -1;  // advanced by every forward call
+  cudaEvent_t ev[kProfSlots][ST_COUNT][2] = {};
+  bool have[kProfSlots][ST_COUNT] = {};
+};
+Profiler g_prof;  // process-wide; profiling is a single-threaded bench facility
+
+void prof_next_call() {
+  if (!g_prof.enabled) return;
+  g_prof.slot = (g_prof.slot + 1) % kProfSlots;
+  for (int i = 0; i < ST_COUNT; ++i) g_prof.have[g_prof.slot][i] = false;
+}
+
+void prof_mark(int stage, int which, cudaStream_t stream) {
+  if (!g_prof.enabled) return;
+  if (!g_prof.created) {
+    for (int k = 0; k < kProfSlots; ++k)
+      for (int i = 0; i < ST_COUNT; ++i)
+        for (int j = 0; j < 2; ++j) cudaEventCreate(&g_prof.ev[k][i][j]);
+    g_prof.created = true;
+  }
+  if (g_prof.slot < 0) g_prof.slot = 0;
+  cudaEventRecord(g_prof.ev[g_prof.slot][stage][which], stream);
+  if (which == 1) g_prof.have[g_prof.slot][stage] = true;
+}
 
 int fail(const std::string& msg) {
   g_last_error = msg;
@@ -135,6 +174,7 @@ int gcr_rasterizer_forward(gcr_alloc_fn geometryBuffer, void* geometry_ctx,
                            int debug, int shard_rank, int shard_count, void* cuda_stream) {
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
   if (P <= 0) return 0;
+  prof_next_call();
   if (width <= 0 || height <= 0) return fail("image size must be positive");
   if (shard_count < 1 || shard_rank < 0 || shard_rank >= shard_count)
     return fail("invalid tile-row shard (rank, count)");
@@ -186,20 +226,27 @@ int gcr_rasterizer_forward(gcr_alloc_fn geometryBuffer, void* geometry_ctx,
   pa.shard_rank = shard_rank; pa.shard_count = shard_count;
   pa.prefiltered = prefiltered != 0;
   pa.radii = radii; pa.tiles_touched = tiles_touched; pa.depth_keys = keys_a;
-  pa.records = records; pa.clamped = clamped; pa.dbg_cov3D = nullptr;
+  pa.records = records; pa.clamped = clamped; pa.dbg_cov3D = g_dbg_cov3d;
+  g_dbg_cov3d = nullptr;
+  prof_mark(ST_PREPROCESS, 0, stream);
   gcr_launch_preprocess_fwd(pa, stream);
   GCR_CHECK_LAUNCH("preprocess_fwd", debug, stream);
+  prof_mark(ST_PREPROCESS, 1, stream);
 
   // 2. stable depth sort of the Gaussians (4 passes: result back in the a buffers)
+  prof_mark(ST_DEPTH_SORT, 0, stream);
   const int side = gcr_launch_radix_sort(keys_a, vals_a, keys_b, vals_b, (size_t)P, 32, true,
                                          gptr + gl.sort_ws, stream);
   GCR_CHECK_LAUNCH("depth sort", debug, stream);
+  prof_mark(ST_DEPTH_SORT, 1, stream);
   uint32_t* sorted_gauss = side ? vals_b : vals_a;
 
   // 3. offsets of each depth-ordered Gaussian's instances
+  prof_mark(ST_SCAN, 0, stream);
   gcr_launch_inclusive_scan(tiles_touched, sorted_gauss, offsets, (size_t)P, gptr + gl.scan_ws,
                             stream);
   GCR_CHECK_LAUNCH("tile-count scan", debug, stream);
+  prof_mark(ST_SCAN, 1, stream);
 
   // 4. R to the host (sizes the binning buffer; same sync as rasterizer_impl.cu:235-238)
   uint32_t num_rendered_u = 0;
@@ -223,17 +270,23 @@ int gcr_rasterizer_forward(gcr_alloc_fn geometryBuffer, void* geometry_ctx,
   GCR_CUDA_OK(cudaMemsetAsync(ranges, 0, sizeof(uint2) * (size_t)tiles, stream));
   if (R > 0) {
     // 5. emit (tile, gaussian) pairs in depth order, 6. stable split by tile id
+    prof_mark(ST_EMIT, 0, stream);
     gcr_launch_emit_pairs(P, sorted_gauss, offsets, tiles_touched, records, radii, grid_x, grid_y,
                           shard_rank, shard_count, tk_a, tv_a, stream);
     GCR_CHECK_LAUNCH("emit pairs", debug, stream);
+    prof_mark(ST_EMIT, 1, stream);
+    prof_mark(ST_TILE_SORT, 0, stream);
     const int tside = gcr_launch_radix_sort(tk_a, tv_a, tk_b, tv_b, R, tile_bits(tiles), false,
                                             bptr + bl.sort_ws, stream);
     GCR_CHECK_LAUNCH("tile sort", debug, stream);
+    prof_mark(ST_TILE_SORT, 1, stream);
     const uint32_t* sorted_keys = tside ? tk_b : tk_a;
     const uint32_t* point_list = tside ? tv_b : tv_a;
     // 7. tile ranges + contiguous per-instance records
+    prof_mark(ST_RANGES_GATHER, 0, stream);
     gcr_launch_ranges_and_gather(R, sorted_keys, point_list, records, ranges, inst, stream);
     GCR_CHECK_LAUNCH("ranges + gather", debug, stream);
+    prof_mark(ST_RANGES_GATHER, 1, stream);
   }
 
   // 8. per-tile blend
@@ -245,8 +298,10 @@ int gcr_rasterizer_forward(gcr_alloc_fn geometryBuffer, void* geometry_ctx,
   ba.final_T = reinterpret_cast<float*>(iptr + il.final_T);
   ba.n_contrib = reinterpret_cast<uint32_t*>(iptr + il.n_contrib);
   ba.out_color = out_color;
+  prof_mark(ST_BLEND_FWD, 0, stream);
   gcr_launch_blend_fwd(ba, stream);
   GCR_CHECK_LAUNCH("blend_fwd", debug, stream);
+  prof_mark(ST_BLEND_FWD, 1, stream);
   return (int)R;
 }
 
@@ -258,7 +313,9 @@ int gcr_rasterizer_backward_blend(int P, int R, const float* background, int wid
   if (P <= 0) return 0;
   if (shard_count < 1 || shard_rank < 0 || shard_rank >= shard_count)
     return fail("invalid tile-row shard (rank, count)");
+  prof_mark(ST_BWD_ZERO, 0, stream);
   GCR_CUDA_OK(cudaMemsetAsync(grad_acc, 0, sizeof(GcrGradAcc) * (size_t)P, stream));
+  prof_mark(ST_BWD_ZERO, 1, stream);
   if (R <= 0) return 0;
   const int grid_x = (width + GCR_TILE_X - 1) / GCR_TILE_X;
   const int grid_y = (height + GCR_TILE_Y - 1) / GCR_TILE_Y;
@@ -277,8 +334,10 @@ int gcr_rasterizer_backward_blend(int P, int R, const float* background, int wid
   ba.n_contrib = reinterpret_cast<uint32_t*>(iptr + il.n_contrib);
   ba.dL_dpix = dL_dpix;
   ba.grad_acc = reinterpret_cast<GcrGradAcc*>(grad_acc);
+  prof_mark(ST_BLEND_BWD, 0, stream);
   gcr_launch_blend_bwd(ba, stream);
   GCR_CHECK_LAUNCH("blend_bwd", debug, stream);
+  prof_mark(ST_BLEND_BWD, 1, stream);
   return 0;
 }
 
@@ -291,9 +350,12 @@ int gcr_rasterizer_backward_geometry(int P, int D, int M, const float* means3D, 
                                      const float* grad_acc, float* dL_dmean2D, float* dL_dconic,
                                      float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D,
                                      float* dL_dcov3D, float* dL_dsh, float* dL_dscale,
-                                     float* dL_drot, int debug, void* cuda_stream) {
+                                     float* dL_drot, int debug, int range_start, int range_count,
+                                     void* cuda_stream) {
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
   if (P <= 0) return 0;
+  if (range_count < 0) { range_start = 0; range_count = P; }
+  if (range_start < 0 || range_start + range_count > P) return fail("Gaussian range out of bounds");
   if (cov3D_precomp == nullptr && (scales == nullptr || rotations == nullptr))
     return fail("provide either scale/rotation or a precomputed 3D covariance");
   if (shs != nullptr && M > 0 && dL_dsh == nullptr) return fail("dL_dsh must not be NULL with SHs");
@@ -302,6 +364,7 @@ int gcr_rasterizer_backward_geometry(int P, int D, int M, const float* means3D, 
   GcrPreprocessBwdArgs a;
   memset(&a, 0, sizeof(a));
   a.P = P; a.D = D; a.M = M;
+  a.range_start = range_start; a.range_count = range_count;
   a.means3D = means3D;
   a.radii = radii != nullptr ? radii : reinterpret_cast<const int*>(gptr + gl.radii);
   a.shs = (M > 0) ? shs : nullptr;
@@ -317,12 +380,18 @@ int gcr_rasterizer_backward_geometry(int P, int D, int M, const float* means3D, 
   a.dL_dcolor = dL_dcolor; a.dL_dmean3D = dL_dmean3D; a.dL_dcov3D = dL_dcov3D;
   a.dL_dsh = dL_dsh; a.dL_dscale = (scales != nullptr) ? dL_dscale : nullptr;
   a.dL_drot = (scales != nullptr) ? dL_drot : nullptr;
+  prof_mark(ST_GEOM_BWD, 0, stream);
   gcr_launch_preprocess_bwd(a, stream);
   GCR_CHECK_LAUNCH("preprocess_bwd", debug, stream);
+  prof_mark(ST_GEOM_BWD, 1, stream);
   // reference semantics: with a precomputed covariance the scale/rotation gradients are zeros
   if (scales == nullptr) {
-    if (dL_dscale) GCR_CUDA_OK(cudaMemsetAsync(dL_dscale, 0, sizeof(float) * 3 * (size_t)P, stream));
-    if (dL_drot) GCR_CUDA_OK(cudaMemsetAsync(dL_drot, 0, sizeof(float) * 4 * (size_t)P, stream));
+    if (dL_dscale)
+      GCR_CUDA_OK(cudaMemsetAsync(dL_dscale + 3 * (size_t)range_start, 0,
+                                  sizeof(float) * 3 * (size_t)range_count, stream));
+    if (dL_drot)
+      GCR_CUDA_OK(cudaMemsetAsync(dL_drot + 4 * (size_t)range_start, 0,
+                                  sizeof(float) * 4 * (size_t)range_count, stream));
   }
   return 0;
 }
@@ -352,7 +421,7 @@ int gcr_rasterizer_backward(int P, int D, int M, int R, const float* background,
                                           height, tan_fovx, tan_fovy, radii, geom_buffer, grad_acc,
                                           dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor,
                                           dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, debug,
-                                          cuda_stream);
+                                          0, -1, cuda_stream);
 }
 
 int gcr_rasterizer_mark_visible(int P, const float* means3D, const float* viewmatrix,
@@ -363,6 +432,36 @@ int gcr_rasterizer_mark_visible(int P, const float* means3D, const float* viewma
   gcr_launch_check_frustum(P, means3D, viewmatrix, reinterpret_cast<bool*>(present), stream);
   GCR_CHECK_LAUNCH("check_frustum", 0, stream);
   return 0;
+}
+
+void gcr_debug_set_cov3d_out(float* cov3d) { g_dbg_cov3d = cov3d; }
+
+void gcr_profile_enable(int on) {
+  g_prof.enabled = on != 0;
+  g_prof.slot = -1;
+  for (int k = 0; k < kProfSlots; ++k)
+    for (int i = 0; i < ST_COUNT; ++i) g_prof.have[k][i] = false;
+}
+int gcr_profile_stage_count(void) { return ST_COUNT; }
+const char* gcr_profile_stage_name(int stage) {
+  return (stage >= 0 && stage < ST_COUNT) ? kStageNames[stage] : "";
+}
+// mean device time of `stage` over the profiled calls since gcr_profile_enable(1)
+float gcr_profile_stage_ms(int stage) {
+  if (stage < 0 || stage >= ST_COUNT || !g_prof.created) return -1.f;
+  double sum = 0.0;
+  int n = 0;
+  for (int k = 0; k < kProfSlots; ++k) {
+    if (!g_prof.have[k][stage]) continue;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g_prof.ev[k][stage][0], g_prof.ev[k][stage][1]) != cudaSuccess) {
+      cudaGetLastError();
+      continue;
+    }
+    sum += ms;
+    ++n;
+  }
+  return n ? (float)(sum / n) : -1.f;
 }
 
 size_t gcr_debug_offset(int which, int P, int R, int width, int height) {

@@ -86,6 +86,7 @@ void gcr_launch_blend_bwd(const GcrBlendArgs& a, cudaStream_t stream);
 // ---- backward preprocess (preprocess_bwd.cu) --------------------------------------------------
 struct GcrPreprocessBwdArgs {
   int P, D, M;
+  int range_start, range_count;  // Gaussians [range_start, range_start+range_count) are processed
   const float* means3D;
   const int* radii;
   const float* shs;

@@ -86,13 +86,15 @@ preprocess_fwd_kernel(GcrPreprocessArgs a) {
       const float4 q = reinterpret_cast<const float4*>(a.rotations)[idx];
       const float r = q.x, x = q.y, y = q.z, z = q.w;
       // R columns (GLM column-major constructor order)
-      const float R00 = __fsub_rn(1.f, __fmul_rn(2.f, __fmaf_rn(y, y, __fmul_rn(z, z))));
+      // (decoded from the reference SASS: shared products are materialised, the other one fused;
+      //  yy + zz is a plain add, xz +- ry fuses r*y onto rn(x*z))
+      const float R00 = __fsub_rn(1.f, __fmul_rn(2.f, __fadd_rn(__fmul_rn(y, y), __fmul_rn(z, z))));
       const float R01 = __fmul_rn(2.f, __fmaf_rn(x, y, -__fmul_rn(r, z)));
-      const float R02 = __fmul_rn(2.f, __fmaf_rn(x, z, __fmul_rn(r, y)));
+      const float R02 = __fmul_rn(2.f, __fmaf_rn(r, y, __fmul_rn(x, z)));
       const float R10 = __fmul_rn(2.f, __fmaf_rn(x, y, __fmul_rn(r, z)));
       const float R11 = __fsub_rn(1.f, __fmul_rn(2.f, __fmaf_rn(x, x, __fmul_rn(z, z))));
       const float R12 = __fmul_rn(2.f, __fmaf_rn(y, z, -__fmul_rn(r, x)));
-      const float R20 = __fmul_rn(2.f, __fmaf_rn(x, z, -__fmul_rn(r, y)));
+      const float R20 = __fmul_rn(2.f, __fmaf_rn(-r, y, __fmul_rn(x, z)));
       const float R21 = __fmul_rn(2.f, __fmaf_rn(y, z, __fmul_rn(r, x)));
       const float R22 = __fsub_rn(1.f, __fmul_rn(2.f, __fmaf_rn(x, x, __fmul_rn(y, y))));
       // M = S * R  ->  M[i][j] = s_j * R[i][j]   (column i, row j)

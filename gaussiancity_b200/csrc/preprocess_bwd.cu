@@ -30,8 +30,9 @@ __forceinline__ __device__ M3 m3_mul(const M3& A, const M3& B) {
 template <bool kHasSH>
 __global__ void __launch_bounds__(256)
 preprocess_bwd_kernel(GcrPreprocessBwdArgs a) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= a.P) return;
+  const int loc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (loc >= a.range_count) return;
+  const int idx = a.range_start + loc;
 
   const bool visible = a.radii[idx] > 0;
   float o_m2x = 0.f, o_m2y = 0.f, o_op = 0.f, o_cr = 0.f, o_cg = 0.f, o_cb = 0.f;
@@ -341,8 +342,8 @@ preprocess_bwd_kernel(GcrPreprocessBwdArgs a) {
 }  // namespace
 
 void gcr_launch_preprocess_bwd(const GcrPreprocessBwdArgs& a, cudaStream_t stream) {
-  if (a.P <= 0) return;
-  const int blocks = (a.P + 255) / 256;
+  if (a.P <= 0 || a.range_count <= 0) return;
+  const int blocks = (a.range_count + 255) / 256;
   if (a.shs != nullptr && a.M > 0)
     preprocess_bwd_kernel<true><<<blocks, 256, 0, stream>>>(a);
   else

@@ -83,7 +83,10 @@ GCR_API int gcr_rasterizer_backward(int P, int D, int M, int R, const float* bac
 
 /* The two halves of gcr_rasterizer_backward, split at the only cross-tile coupling so that a
  * tile-sharded job can reduce between them.  grad_acc is [P,12] fp32 (48 B per Gaussian:
- * dmean2D.xy, dconic.xyw, dopacity, dcolor.rgb, 3 pad), zeroed by _blend before accumulation. */
+ * dmean2D.xy, dconic.xyw, dopacity, dcolor.rgb, 3 pad), zeroed by _blend before accumulation.
+ * _geometry processes Gaussians [range_start, range_start + range_count) only (all pointers are
+ * bases of the full [P,...] arrays; range_count < 0 means all): after a reduce-scatter each rank
+ * finishes its own slice. */
 GCR_API int gcr_rasterizer_backward_blend(int P, int R, const float* background, int width, int height,
                                   char* binning_buffer, char* image_buffer, const float* dL_dpix,
                                   float* grad_acc, int debug, int shard_rank, int shard_count,
@@ -97,7 +100,8 @@ GCR_API int gcr_rasterizer_backward_geometry(int P, int D, int M, const float* m
                                      const float* grad_acc, float* dL_dmean2D, float* dL_dconic,
                                      float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D,
                                      float* dL_dcov3D, float* dL_dsh, float* dL_dscale,
-                                     float* dL_drot, int debug, void* cuda_stream);
+                                     float* dL_drot, int debug, int range_start, int range_count,
+                                     void* cuda_stream);
 
 /* present: P bytes (bool). Returns 0 or < 0. */
 GCR_API int gcr_rasterizer_mark_visible(int P, const float* means3D, const float* viewmatrix,
@@ -127,6 +131,19 @@ enum {
   GCR_IMG_TOTAL_BYTES = 500
 };
 GCR_API size_t gcr_debug_offset(int which, int P, int R, int width, int height);
+/* test hook: the NEXT gcr_rasterizer_forward on this thread also stores the per-Gaussian 3D
+ * covariance ([P,6] fp32, device) it computed (the reference keeps it in geomBuffer). */
+GCR_API void gcr_debug_set_cov3d_out(float* cov3d);
+
+/* ---- per-stage device timing (bench.py) ------------------------------------------------------
+ * When enabled, every pipeline stage of the next forward / backward call is bracketed by CUDA
+ * events recorded on the caller's stream (no synchronisation is added).  After the caller has
+ * synchronised, gcr_profile_stage_ms(i) is the device time of stage i of the most recent call
+ * (-1 if the stage did not run).  Stage names: gcr_profile_stage_name(i), i < stage_count. */
+GCR_API void gcr_profile_enable(int on);
+GCR_API int gcr_profile_stage_count(void);
+GCR_API const char* gcr_profile_stage_name(int stage);
+GCR_API float gcr_profile_stage_ms(int stage);
 
 #ifdef __cplusplus
 }
