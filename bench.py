@@ -1,0 +1,429 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native Gaussian rasterizer hot path.
+
+Metric (BASELINE.json): Msplats/s = P / t(fwd+bwd) / 1e6 on synthetic Gaussian clouds; also the
+rendered MPix/s of the forward alone and the roofline fraction of the dominant kernel.
+Default workload (N=1): BASELINE config 4 -- 5 M Gaussians, SH degree 3, 1920x1080, fwd+bwd on
+ONE GPU (it fits: ~4 GB).  `--workload` selects the smaller parity configs.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One JSON line on stdout (rank 0).  Timing: W untimed warm-up steps, then exactly K steps
+bracketed by barrier + torch.cuda.synchronize(), CUDA events on the launching stream, max over
+ranks.  `value` is measured with inputs resident in HBM; `e2e` is the same metric through the
+public API with HOST (pinned) buffers, host->device copies of every input and a device->host
+read of the rendered image and loss inside the timed region.
+`--impl reference` runs the UNMODIFIED reference CUDA extension (oracle/_ref, built from
+/root/reference by oracle/build_ref.py) on the same workload through the same harness; if it is
+not available the CPU oracle port is timed instead on a bounded sample.
+Inputs (1.2 GB at the default workload) are far larger than the 126 MB L2, so no explicit L2
+flush is needed between timed iterations (stated in config.l2).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+WORKLOADS = {
+    # name: (P, W, H, sh_degree, use_sh)
+    "cfg4_5M_sh3_1080p": (5_000_000, 1920, 1080, 3, True),
+    "cfg3_1M_sh3_1080p": (1_000_000, 1920, 1080, 3, True),
+    "cfg2_100k_sh0_512": (100_000, 512, 512, 0, True),
+    "city_5M_precomp_1080p": (5_000_000, 1920, 1080, 0, False),
+    "tiny": (20_000, 256, 256, 1, True),
+}
+DEFAULT_WORKLOAD = "cfg4_5M_sh3_1080p"
+
+
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu_index = gpu_index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def tile_sort_passes(W, H):
+    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    bits = max(1, (tiles - 1).bit_length())
+    return (bits + 7) // 8
+
+
+def kernels_per_step(W, H, backward=True):
+    """Kernels of OUR library launched by one forward(+backward) (memsets excluded)."""
+    fwd = 1 + 4 * 3 + 3 + 1 + tile_sort_passes(W, H) * 3 + 1 + 1
+    return fwd + (2 if backward else 0)
+
+
+# ------------------------------------------------------------------------------------------
+def make_scene(name, device):
+    from gaussiancity_b200.synthetic import uniform_scene
+    P, W, H, deg, use_sh = WORKLOADS[name]
+    return uniform_scene(P, W, H, sh_degree=deg, seed=0, device=device, use_sh=use_sh)
+
+
+def scene_inputs(s):
+    e = torch.Tensor([])
+    return dict(bg=s.bg, means3D=s.means3D, colors=s.colors_precomp if s.colors_precomp is not None else e,
+                opacity=s.opacities, scales=s.scales, rotations=s.rotations,
+                sh=s.shs if s.shs is not None else e, view=s.view_matrix, proj=s.proj_matrix,
+                campos=s.campos)
+
+
+def fwd_args(s, inp):
+    e = torch.Tensor([])
+    return (inp["bg"], inp["means3D"], inp["colors"], inp["opacity"], inp["scales"], inp["rotations"],
+            1.0, e, inp["view"], inp["proj"], s.tanfovx, s.tanfovy, s.img_h, s.img_w, inp["sh"],
+            s.sh_degree, inp["campos"], False, False)
+
+
+def bwd_args(s, inp, radii, grad_out, geom, R, binning, img):
+    e = torch.Tensor([])
+    return (inp["bg"], inp["means3D"], radii, inp["colors"], inp["scales"], inp["rotations"], 1.0, e,
+            inp["view"], inp["proj"], s.tanfovx, s.tanfovy, grad_out, inp["sh"], s.sh_degree,
+            inp["campos"], geom, R, binning, img, False)
+
+
+def time_steps(step, steps, warmup, barrier):
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    return e0.elapsed_time(e1) / steps
+
+
+def max_over_ranks(x, device, world):
+    if world == 1:
+        return x
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+# ------------------------------------------------------------------------------------------
+def run_gpu_arm(args, impl, rank, world, device):
+    s = make_scene(args.workload, device)
+    P, W, H = s.means3D.shape[0], s.img_w, s.img_h
+    inp = scene_inputs(s)
+    g = torch.Generator().manual_seed(123)
+    grad_out = torch.randn(3, H, W, generator=g).to(device)
+    barrier = (lambda: dist.barrier()) if world > 1 else (lambda: None)
+    extra = {}
+
+    if impl == "ours":
+        from gaussiancity_b200 import _cabi, ext
+        _cabi.lib()  # fail loudly if the CUDA library is missing
+        if world > 1:
+            from gaussiancity_b200 import sharding
+            eng = sharding.TileShardedRasterizer(device=device)
+
+            def step():
+                return eng.forward_backward(s, inp, grad_out, src=0)
+            fwd_only = lambda: eng.forward(s, inp, src=0)
+            ms = max_over_ranks(time_steps(step, args.steps, args.warmup, barrier), device, world)
+            ms_fwd = max_over_ranks(time_steps(fwd_only, max(2, args.steps // 2), 1, barrier), device, world)
+            R = eng.last_num_rendered_total
+            return dict(ms=ms, ms_fwd=ms_fwd, R=R, V=None, stages=None, P=P, W=W, H=H, s=s, inp=inp,
+                        grad_out=grad_out, extra={"parallelism": f"tile-row shard x{world} (NCCL broadcast + reduce_scatter)"})
+        mod = ext
+    else:
+        from tests import refext
+        mod = refext.load_reference_ext()
+        if mod is None:
+            return None
+
+    state = {}
+
+    def step():
+        R, color, radii, geom, binning, img = mod.rasterize_gaussians(*fwd_args(s, inp))
+        grads = mod.rasterize_gaussians_backward(*bwd_args(s, inp, radii, grad_out, geom, R, binning, img))
+        state["R"], state["radii"], state["grads"], state["color"] = R, radii, grads, color
+
+    def fwd_only():
+        state["fwd"] = mod.rasterize_gaussians(*fwd_args(s, inp))
+
+    # warm up first (lazy module loading, allocator), then profile exactly the timed steps
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if impl == "ours":
+        _cabi.profile_enable(True)
+    ms = time_steps(step, args.steps, 0, barrier)
+    stages = None
+    if impl == "ours":
+        stages = _cabi.profile_read()
+        _cabi.profile_enable(False)
+    ms_fwd = time_steps(fwd_only, max(2, args.steps // 2), 3, barrier)
+    R = int(state["R"])
+    V = int((state["radii"] > 0).sum().item())
+    return dict(ms=ms, ms_fwd=ms_fwd, R=R, V=V, stages=stages, P=P, W=W, H=H, s=s, inp=inp,
+                grad_out=grad_out, extra=extra)
+
+
+def run_e2e(args, impl, res, device):
+    """Same metric through the public API with HOST buffers: per step, H2D of every input from
+    pinned memory, forward + backward, D2H of the rendered image and the loss."""
+    s, P, W, H = res["s"], res["P"], res["W"], res["H"]
+    host = {k: (v.cpu().pin_memory() if v.numel() else v) for k, v in res["inp"].items()}
+    dev = {k: (torch.empty_like(v, device=device) if v.numel() else v) for k, v in host.items()}
+    grad_out = res["grad_out"]
+    host_img = torch.empty(3, H, W, dtype=torch.float32).pin_memory()
+    host_loss = torch.empty(1, dtype=torch.float32).pin_memory()
+    h2d = sum(v.numel() * v.element_size() for v in host.values() if v.numel())
+    d2h = host_img.numel() * 4 + 4
+
+    if impl == "ours":
+        from gaussiancity_b200 import GaussianRasterizationSettings, GaussianRasterizer
+
+        def step():
+            for k, v in host.items():
+                if v.numel():
+                    dev[k].copy_(v, non_blocking=True)
+            settings = GaussianRasterizationSettings(
+                img_h=H, img_w=W, tanfovx=s.tanfovx, tanfovy=s.tanfovy, bg=dev["bg"], scale_modifier=1.0,
+                view_matrix=dev["view"], proj_matrix=dev["proj"], sh_degree=s.sh_degree,
+                campos=dev["campos"], prefiltered=False, debug=False)
+            leaves = {k: dev[k].requires_grad_(True) for k in ("means3D", "opacity", "scales", "rotations")}
+            has_sh = dev["sh"].numel() > 0
+            col_leaf = (dev["sh"] if has_sh else dev["colors"]).requires_grad_(True)
+            means2D = torch.zeros_like(dev["means3D"], requires_grad=True)
+            color, _ = GaussianRasterizer(settings)(
+                leaves["means3D"], means2D, leaves["opacity"], shs=col_leaf if has_sh else None,
+                colors_precomp=None if has_sh else col_leaf, scales=leaves["scales"],
+                rotations=leaves["rotations"])
+            loss = (color * grad_out).sum()
+            loss.backward()
+            host_img.copy_(color.detach(), non_blocking=True)
+            host_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+            for t in list(leaves.values()) + [col_leaf]:
+                t.grad = None
+                t.requires_grad_(False)
+    else:
+        from tests import refext
+        mod = refext.load_reference_ext()
+
+        def step():
+            for k, v in host.items():
+                if v.numel():
+                    dev[k].copy_(v, non_blocking=True)
+            R, color, radii, geom, binning, img = mod.rasterize_gaussians(*fwd_args(s, dev))
+            loss = (color * grad_out).sum()
+            mod.rasterize_gaussians_backward(*bwd_args(s, dev, radii, grad_out, geom, R, binning, img))
+            host_img.copy_(color, non_blocking=True)
+            host_loss.copy_(loss.reshape(1), non_blocking=True)
+
+    ms = time_steps(step, max(2, args.steps // 2), 2, lambda: None)
+    return {"value": P / (ms * 1e-3) / 1e6, "unit": "Msplats/s", "ms_per_step": ms,
+            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
+
+
+def run_cpu_baseline(workload, budget_s=20.0):
+    """CPU oracle port (oracle/gs_oracle.c, OpenMP in the blend stages) on a bounded sample of
+    the same workload: the first `n` Gaussians at full resolution, forward + backward."""
+    import numpy as np
+    from gaussiancity_b200.synthetic import uniform_scene
+    from oracle import oracle as cpu_oracle
+    P, W, H, deg, use_sh = WORKLOADS[workload]
+    n = min(P, 200_000)
+    s = uniform_scene(n, W, H, sh_degree=deg, seed=0, device="cpu", use_sh=use_sh)
+    G = np.random.default_rng(0).standard_normal((3, H, W)).astype(np.float32)
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    t0 = time.time()
+    reps = 0
+    while True:
+        r = cpu_oracle.forward_scene(s, "f32")
+        cpu_oracle.backward(r, G)
+        reps += 1
+        if time.time() - t0 > budget_s * 0.5 or reps >= 3:
+            break
+    dt = (time.time() - t0) / reps
+    return {"value": n / dt / 1e6, "unit": "Msplats/s", "cores": cores, "kind": "port",
+            "sample": f"first {n} Gaussians of {workload} at {W}x{H}, fwd+bwd, {reps} rep(s), "
+                      f"{dt:.2f} s each (oracle/gs_oracle.c fp32; preprocess+sort serial, blend OpenMP)"}
+
+
+# ------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default=DEFAULT_WORKLOAD)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: this benchmark has no CPU path"}))
+        sys.exit(1)
+    device = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(device)
+
+    if args.impl == "reference" and world > 1:
+        # reference arm: rank 0 alone runs and prints; the other ranks exit without work
+        if rank != 0:
+            return
+        world_eff = 1
+    else:
+        world_eff = world
+        if world > 1:
+            dist.init_process_group(backend="nccl", device_id=device)
+
+    P, W, H, deg, use_sh = WORKLOADS[args.workload]
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    res = run_gpu_arm(args, args.impl, rank, world_eff, device)
+    clocks = sampler.stop() if rank == 0 else None
+
+    line = {"metric": "Msplats/s fwd+bwd", "unit": "Msplats/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
+            "vs_baseline": None}
+    config = {"workload": args.workload, "gaussians": P, "image": f"{W}x{H}", "sh_degree": deg,
+              "colour_path": "sh" if use_sh else "colors_precomp", "pass": "forward+backward",
+              "l2": "inputs (44+12M B/Gaussian = %.2f GB) exceed the 126 MB L2; no explicit flush"
+                    % ((44 + (12 * (deg + 1) ** 2 if use_sh else 12)) * P / 1e9)}
+
+    if res is None:
+        # reference extension unavailable -> CPU oracle port on a bounded sample
+        if rank == 0:
+            cb = run_cpu_baseline(args.workload)
+            line.update({"impl": "reference", "value": cb["value"], "ms_per_step": None,
+                         "scaling": "strong", "config": config, "cpu_baseline": cb,
+                         "e2e": {"value": cb["value"], "unit": cb["unit"], "h2d_bytes_per_step": 0,
+                                 "d2h_bytes_per_step": 0},
+                         "note": "oracle/_ref not built: timed the CPU oracle port instead"})
+            print(json.dumps(line))
+        return
+
+    ms, ms_fwd, R, V = res["ms"], res["ms_fwd"], res["R"], res["V"]
+    if rank == 0:
+        value = P / (ms * 1e-3) / 1e6
+        line.update({"value": value, "ms_per_step": ms, "scaling": "strong" if world_eff > 1 else "weak",
+                     "mpix_per_s_forward": W * H / (ms_fwd * 1e-3) / 1e6, "ms_forward": ms_fwd,
+                     "num_rendered": R, "visible": V,
+                     "mean_tile_list": R / (((W + 15) // 16) * ((H + 15) // 16))})
+        if args.impl == "reference":
+            line["impl"] = "reference"
+            line["gpu_launches"] = 0
+            config["reference"] = "unmodified DGR CUDA extension (oracle/_ref) on 1 B200, native entry points"
+            line["cpu_baseline"] = {"value": value, "unit": "Msplats/s", "cores": 0, "kind": "reference",
+                                    "sample": "full workload on the GPU: the reference has no CPU "
+                                              "implementation of this path (SURVEY.md 8c)"}
+        else:
+            line["gpu_launches"] = kernels_per_step(W, H) * args.steps if world_eff == 1 else None
+            config.update(res["extra"])
+            if world_eff == 1:
+                config["parallelism"] = "single GPU"
+        # roofline of the dominant kernel (per-stage CUDA events over the timed region)
+        peak, peak_src = load_peaks()
+        stages = res["stages"]
+        if stages:
+            T = ((W + 15) // 16) * ((H + 15) // 16)
+            Npix = W * H
+            alg = {"blend_bwd": 8 * T + 40 * R + 20 * Npix + 44 * (V or 0),
+                   "blend_fwd": 8 * T + 40 * R + 20 * Npix}
+            dom = max(("blend_bwd", "blend_fwd"), key=lambda k: stages.get(k, 0.0))
+            dur = stages[dom]
+            achieved = alg[dom] / (dur * 1e-3) / 1e9
+            line["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak,
+                                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                                "peak_source": peak_src, "kernel_ms": dur,
+                                "algorithmic_bytes": alg[dom],
+                                "note": "blend kernels are fp32-issue/L2-reduction bound (~160 FLOP "
+                                        "per algorithmic byte); see DESIGN.md and profiles/"}
+            line["stage_ms"] = stages
+        line["clocks"] = clocks
+        line["config"] = config
+
+    if world_eff == 1 and not args.no_e2e:
+        e2e = run_e2e(args, args.impl, res, device)
+        if rank == 0:
+            line["e2e"] = e2e
+    if rank == 0 and args.impl == "ours" and world_eff == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = run_cpu_baseline(args.workload)
+    if rank == 0:
+        print(json.dumps(line))
+    if world_eff > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

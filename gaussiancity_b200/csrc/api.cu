@@ -9,7 +9,9 @@
 //   per-Gaussian geometry backward that writes every output exactly once.
 // Everything is launched on the caller's stream; the only host synchronisation is the 4-byte
 // read of R that sizes the binning buffer (the reference has the same one, :235-238).
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -59,6 +61,23 @@ void prof_mark(int stage, int which, cudaStream_t stream) {
   cudaEventRecord(g_prof.ev[g_prof.slot][stage][which], stream);
   if (which == 1) g_prof.have[g_prof.slot][stage] = true;
 }
+
+// host-side phase timing to stderr when GCR_HOST_TIMING=1 (diagnostics only)
+struct HostTimer {
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  std::string log;
+  HostTimer() : on(getenv("GCR_HOST_TIMING") != nullptr), t0(std::chrono::steady_clock::now()) {}
+  void lap(const char* what) {
+    if (!on) return;
+    auto t1 = std::chrono::steady_clock::now();
+    char buf[96];
+    snprintf(buf, sizeof(buf), " %s=%.3f", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    log += buf;
+    t0 = t1;
+  }
+  ~HostTimer() { if (on) fprintf(stderr, "[gcr host ms]%s\n", log.c_str()); }
+};
 
 int fail(const std::string& msg) {
   g_last_error = msg;
@@ -192,6 +211,7 @@ int gcr_rasterizer_forward(gcr_alloc_fn geometryBuffer, void* geometry_ctx,
   const int tiles = grid_x * grid_y;
   const size_t npix = (size_t)width * height;
 
+  HostTimer ht;
   const GeomLayout gl((size_t)P);
   char* gptr = geometryBuffer(geometry_ctx, gl.total);
   if (gptr == nullptr) return fail("geometry buffer allocation failed");
@@ -201,6 +221,7 @@ int gcr_rasterizer_forward(gcr_alloc_fn geometryBuffer, void* geometry_ctx,
   if (iptr == nullptr) return fail("image buffer allocation failed");
   iptr = align256(iptr);
 
+  ht.lap("alloc_geom_img");
   uint32_t* keys_a = reinterpret_cast<uint32_t*>(gptr + gl.keys_a);
   uint32_t* keys_b = reinterpret_cast<uint32_t*>(gptr + gl.keys_b);
   uint32_t* vals_a = reinterpret_cast<uint32_t*>(gptr + gl.vals_a);
@@ -249,10 +270,12 @@ int gcr_rasterizer_forward(gcr_alloc_fn geometryBuffer, void* geometry_ctx,
   prof_mark(ST_SCAN, 1, stream);
 
   // 4. R to the host (sizes the binning buffer; same sync as rasterizer_impl.cu:235-238)
+  ht.lap("launch_pre");
   uint32_t num_rendered_u = 0;
   GCR_CUDA_OK(cudaMemcpyAsync(&num_rendered_u, offsets + (P - 1), sizeof(uint32_t),
                               cudaMemcpyDeviceToHost, stream));
   GCR_CUDA_OK(cudaStreamSynchronize(stream));
+  ht.lap("sync_R");
   if (num_rendered_u > 0x7fffffffu) return fail("num_rendered exceeds int32");
   const size_t R = num_rendered_u;
 
@@ -260,6 +283,7 @@ int gcr_rasterizer_forward(gcr_alloc_fn geometryBuffer, void* geometry_ctx,
   char* bptr = binningBuffer(binning_ctx, bl.total);
   if (bptr == nullptr) return fail("binning buffer allocation failed");
   bptr = align256(bptr);
+  ht.lap("alloc_bin");
   uint32_t* tk_a = reinterpret_cast<uint32_t*>(bptr + bl.keys_a);
   uint32_t* tk_b = reinterpret_cast<uint32_t*>(bptr + bl.keys_b);
   uint32_t* tv_a = reinterpret_cast<uint32_t*>(bptr + bl.vals_a);
@@ -302,6 +326,7 @@ int gcr_rasterizer_forward(gcr_alloc_fn geometryBuffer, void* geometry_ctx,
   gcr_launch_blend_fwd(ba, stream);
   GCR_CHECK_LAUNCH("blend_fwd", debug, stream);
   prof_mark(ST_BLEND_FWD, 1, stream);
+  ht.lap("launch_post");
   return (int)R;
 }
 

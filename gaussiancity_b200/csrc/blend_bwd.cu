@@ -24,6 +24,38 @@ __forceinline__ __device__ float warp_sum(float v) {
   return v;
 }
 
+// Sum 8 per-lane values across the warp with 4+2+1+1+1 = 9 shuffles (instead of 8 x 5): at
+// each of the first three butterfly levels a lane keeps half of its values and ships the other
+// half to its partner.  Afterwards lane L with L % 4 == 0 holds the warp total of value
+//   q(L) = 4*bit4(L) + 2*bit3(L) + bit2(L).
+__forceinline__ __device__ float warp_sum8_scatter(float a0, float a1, float a2, float a3,
+                                                   float a4, float a5, float a6, float a7,
+                                                   int lane) {
+  const bool u16 = (lane & 16) != 0;
+  // level 16: lower half keeps a0..a3, upper half keeps a4..a7
+  float k0 = u16 ? a4 : a0, s0 = u16 ? a0 : a4;
+  float k1 = u16 ? a5 : a1, s1 = u16 ? a1 : a5;
+  float k2 = u16 ? a6 : a2, s2 = u16 ? a2 : a6;
+  float k3 = u16 ? a7 : a3, s3 = u16 ? a3 : a7;
+  k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+  k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+  k2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+  k3 += __shfl_xor_sync(0xffffffffu, s3, 16);
+  // level 8: keep (k0,k1) or (k2,k3)
+  const bool u8 = (lane & 8) != 0;
+  float m0 = u8 ? k2 : k0, t0 = u8 ? k0 : k2;
+  float m1 = u8 ? k3 : k1, t1 = u8 ? k1 : k3;
+  m0 += __shfl_xor_sync(0xffffffffu, t0, 8);
+  m1 += __shfl_xor_sync(0xffffffffu, t1, 8);
+  // level 4: keep m0 or m1
+  const bool u4 = (lane & 4) != 0;
+  float v = u4 ? m1 : m0, w = u4 ? m0 : m1;
+  v += __shfl_xor_sync(0xffffffffu, w, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v;
+}
+
 __global__ void __launch_bounds__(kBlendThreads)
 blend_bwd_kernel(GcrBlendArgs a) {
   __shared__ __align__(128) GcrRecord stage[kBlendStages][kBlendBatch];
@@ -135,7 +167,9 @@ blend_bwd_kernel(GcrBlendArgs a) {
               const float alpha = fminf(0.99f, __fmul_rn(r1.y, G));
               if (!(alpha < 1.0f / 255.0f)) {
                 contrib = true;
-                T = T / (1.f - alpha);
+                // one IEEE reciprocal serves both divisions by (1 - alpha) (<= 1 ulp from x / y)
+                const float inv_1ma = __frcp_rn(1.f - alpha);
+                T = T * inv_1ma;
                 const float dchannel_dcolor = alpha * T;
                 float dL_dalpha = 0.f;
                 acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0;
@@ -152,7 +186,7 @@ blend_bwd_kernel(GcrBlendArgs a) {
                 g_b = dchannel_dcolor * dLp2;
                 dL_dalpha *= T;
                 last_alpha = alpha;
-                dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+                dL_dalpha += (-T_final * inv_1ma) * bg_dot_dpixel;
 
                 const float dL_dG = r1.y * dL_dalpha;
                 const float gdx = G * dx;
@@ -169,20 +203,14 @@ blend_bwd_kernel(GcrBlendArgs a) {
             }
           }
           if (__ballot_sync(0xffffffffu, contrib) != 0u) {
-            g_mx = warp_sum(g_mx);
-            g_my = warp_sum(g_my);
-            g_ca = warp_sum(g_ca);
-            g_cb = warp_sum(g_cb);
-            g_cc = warp_sum(g_cc);
-            g_op = warp_sum(g_op);
-            g_r = warp_sum(g_r);
-            g_g = warp_sum(g_g);
-            g_b = warp_sum(g_b);
-            if (lane == 0) {
-              GcrGradAcc* dst = a.grad_acc + __float_as_uint(r2.y);
-              gcr_red_add_v4(&dst->g0, g_mx, g_my, g_ca, g_cb);
-              gcr_red_add_v4(&dst->g1, g_cc, g_op, g_r, g_g);
-              atomicAdd(&dst->g2.x, g_b);
+            // accumulator float layout: 0 mean2D.x, 1 mean2D.y, 2 conic.x, 3 conic.y,
+            // 4 conic.w, 5 opacity, 6 colour.r, 7 colour.g, 8 colour.b
+            const float tot = warp_sum8_scatter(g_mx, g_my, g_ca, g_cb, g_cc, g_op, g_r, g_g, lane);
+            const float tot_b = warp_sum(g_b);
+            if ((lane & 3) == 0 || lane == 1) {
+              const int q = (lane == 1) ? 8 : (((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1));
+              float* dst = reinterpret_cast<float*>(a.grad_acc + __float_as_uint(r2.y)) + q;
+              atomicAdd(dst, (lane == 1) ? tot_b : tot);
             }
           }
         }

@@ -194,88 +194,84 @@ preprocess_bwd_kernel(GcrPreprocessBwdArgs a) {
       const float x = dox / len, y = doy / len, z = doz / len;
       const uint8_t cl = a.clamped[idx];
       float dRGB[3] = {(cl & 1) ? 0.f : o_cr, (cl & 2) ? 0.f : o_cg, (cl & 4) ? 0.f : o_cb};
-      const float* __restrict__ sh = a.shs + shbase;
-      float* __restrict__ dsh = a.dL_dsh + shbase;
-      float dRGBdx[3] = {0, 0, 0}, dRGBdy[3] = {0, 0, 0}, dRGBdz[3] = {0, 0, 0};
-#define SH(k, ch) __ldg(sh + 3 * (k) + (ch))
-#define DSH(k, v)                                  \
-  {                                                \
-    dsh[3 * (k) + 0] = (v) * dRGB[0];              \
-    dsh[3 * (k) + 1] = (v) * dRGB[1];              \
-    dsh[3 * (k) + 2] = (v) * dRGB[2];              \
-  }
-      DSH(0, GCR_SH_C0);
-      if (a.D > 0) {
-        DSH(1, -GCR_SH_C1 * y);
-        DSH(2, GCR_SH_C1 * z);
-        DSH(3, -GCR_SH_C1 * x);
+      // Basis b[k] and its partial derivatives (x, y, z treated as independent, exactly the
+      // reference's dRGBd{x,y,z} terms); bands above the active degree are zeroed so their
+      // coefficients receive zero gradient (the reference leaves torch::zeros there).
+      float b[16], bx[16], by[16], bz[16];
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-          dRGBdx[ch] = -GCR_SH_C1 * SH(3, ch);
-          dRGBdy[ch] = -GCR_SH_C1 * SH(1, ch);
-          dRGBdz[ch] = GCR_SH_C1 * SH(2, ch);
-        }
+      for (int k = 0; k < 16; ++k) { b[k] = 0.f; bx[k] = 0.f; by[k] = 0.f; bz[k] = 0.f; }
+      b[0] = GCR_SH_C0;
+      if (a.D > 0) {
+        b[1] = -GCR_SH_C1 * y; by[1] = -GCR_SH_C1;
+        b[2] = GCR_SH_C1 * z;  bz[2] = GCR_SH_C1;
+        b[3] = -GCR_SH_C1 * x; bx[3] = -GCR_SH_C1;
         if (a.D > 1) {
           const float xx = x * x, yy = y * y, zz = z * z;
           const float xy = x * y, yz = y * z, xz = x * z;
-          DSH(4, GCR_SH_C2[0] * xy);
-          DSH(5, GCR_SH_C2[1] * yz);
-          DSH(6, GCR_SH_C2[2] * (2.f * zz - xx - yy));
-          DSH(7, GCR_SH_C2[3] * xz);
-          DSH(8, GCR_SH_C2[4] * (xx - yy));
-#pragma unroll
-          for (int ch = 0; ch < 3; ++ch) {
-            dRGBdx[ch] += GCR_SH_C2[0] * y * SH(4, ch) + GCR_SH_C2[2] * 2.f * -x * SH(6, ch) +
-                          GCR_SH_C2[3] * z * SH(7, ch) + GCR_SH_C2[4] * 2.f * x * SH(8, ch);
-            dRGBdy[ch] += GCR_SH_C2[0] * x * SH(4, ch) + GCR_SH_C2[1] * z * SH(5, ch) +
-                          GCR_SH_C2[2] * 2.f * -y * SH(6, ch) + GCR_SH_C2[4] * 2.f * -y * SH(8, ch);
-            dRGBdz[ch] += GCR_SH_C2[1] * y * SH(5, ch) + GCR_SH_C2[2] * 2.f * 2.f * z * SH(6, ch) +
-                          GCR_SH_C2[3] * x * SH(7, ch);
-          }
+          b[4] = GCR_SH_C2[0] * xy; bx[4] = GCR_SH_C2[0] * y; by[4] = GCR_SH_C2[0] * x;
+          b[5] = GCR_SH_C2[1] * yz; by[5] = GCR_SH_C2[1] * z; bz[5] = GCR_SH_C2[1] * y;
+          b[6] = GCR_SH_C2[2] * (2.f * zz - xx - yy);
+          bx[6] = GCR_SH_C2[2] * 2.f * -x; by[6] = GCR_SH_C2[2] * 2.f * -y; bz[6] = GCR_SH_C2[2] * 2.f * 2.f * z;
+          b[7] = GCR_SH_C2[3] * xz; bx[7] = GCR_SH_C2[3] * z; bz[7] = GCR_SH_C2[3] * x;
+          b[8] = GCR_SH_C2[4] * (xx - yy); bx[8] = GCR_SH_C2[4] * 2.f * x; by[8] = GCR_SH_C2[4] * 2.f * -y;
           if (a.D > 2) {
-            DSH(9, GCR_SH_C3[0] * y * (3.f * xx - yy));
-            DSH(10, GCR_SH_C3[1] * xy * z);
-            DSH(11, GCR_SH_C3[2] * y * (4.f * zz - xx - yy));
-            DSH(12, GCR_SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy));
-            DSH(13, GCR_SH_C3[4] * x * (4.f * zz - xx - yy));
-            DSH(14, GCR_SH_C3[5] * z * (xx - yy));
-            DSH(15, GCR_SH_C3[6] * x * (xx - 3.f * yy));
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
-              dRGBdx[ch] += GCR_SH_C3[0] * SH(9, ch) * 3.f * 2.f * xy +
-                            GCR_SH_C3[1] * SH(10, ch) * yz + GCR_SH_C3[2] * SH(11, ch) * -2.f * xy +
-                            GCR_SH_C3[3] * SH(12, ch) * -3.f * 2.f * xz +
-                            GCR_SH_C3[4] * SH(13, ch) * (-3.f * xx + 4.f * zz - yy) +
-                            GCR_SH_C3[5] * SH(14, ch) * 2.f * xz +
-                            GCR_SH_C3[6] * SH(15, ch) * 3.f * (xx - yy);
-              dRGBdy[ch] += GCR_SH_C3[0] * SH(9, ch) * 3.f * (xx - yy) +
-                            GCR_SH_C3[1] * SH(10, ch) * xz +
-                            GCR_SH_C3[2] * SH(11, ch) * (-3.f * yy + 4.f * zz - xx) +
-                            GCR_SH_C3[3] * SH(12, ch) * -3.f * 2.f * yz +
-                            GCR_SH_C3[4] * SH(13, ch) * -2.f * xy +
-                            GCR_SH_C3[5] * SH(14, ch) * -2.f * yz +
-                            GCR_SH_C3[6] * SH(15, ch) * -3.f * 2.f * xy;
-              dRGBdz[ch] += GCR_SH_C3[1] * SH(10, ch) * xy +
-                            GCR_SH_C3[2] * SH(11, ch) * 4.f * 2.f * yz +
-                            GCR_SH_C3[3] * SH(12, ch) * 3.f * (2.f * zz - xx - yy) +
-                            GCR_SH_C3[4] * SH(13, ch) * 4.f * 2.f * xz +
-                            GCR_SH_C3[5] * SH(14, ch) * (xx - yy);
-            }
+            b[9] = GCR_SH_C3[0] * y * (3.f * xx - yy);
+            bx[9] = GCR_SH_C3[0] * 3.f * 2.f * xy; by[9] = GCR_SH_C3[0] * 3.f * (xx - yy);
+            b[10] = GCR_SH_C3[1] * xy * z;
+            bx[10] = GCR_SH_C3[1] * yz; by[10] = GCR_SH_C3[1] * xz; bz[10] = GCR_SH_C3[1] * xy;
+            b[11] = GCR_SH_C3[2] * y * (4.f * zz - xx - yy);
+            bx[11] = GCR_SH_C3[2] * -2.f * xy; by[11] = GCR_SH_C3[2] * (-3.f * yy + 4.f * zz - xx);
+            bz[11] = GCR_SH_C3[2] * 4.f * 2.f * yz;
+            b[12] = GCR_SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
+            bx[12] = GCR_SH_C3[3] * -3.f * 2.f * xz; by[12] = GCR_SH_C3[3] * -3.f * 2.f * yz;
+            bz[12] = GCR_SH_C3[3] * 3.f * (2.f * zz - xx - yy);
+            b[13] = GCR_SH_C3[4] * x * (4.f * zz - xx - yy);
+            bx[13] = GCR_SH_C3[4] * (-3.f * xx + 4.f * zz - yy); by[13] = GCR_SH_C3[4] * -2.f * xy;
+            bz[13] = GCR_SH_C3[4] * 4.f * 2.f * xz;
+            b[14] = GCR_SH_C3[5] * z * (xx - yy);
+            bx[14] = GCR_SH_C3[5] * 2.f * xz; by[14] = GCR_SH_C3[5] * -2.f * yz; bz[14] = GCR_SH_C3[5] * (xx - yy);
+            b[15] = GCR_SH_C3[6] * x * (xx - 3.f * yy);
+            bx[15] = GCR_SH_C3[6] * 3.f * (xx - yy); by[15] = GCR_SH_C3[6] * -3.f * 2.f * xy;
           }
         }
       }
-      // coefficients above the active degree receive zero gradient
-      {
-        const int used = (a.D + 1) * (a.D + 1);
-        for (int k = used; k < a.M; ++k) {
-          dsh[3 * k + 0] = 0.f; dsh[3 * k + 1] = 0.f; dsh[3 * k + 2] = 0.f;
+      // One pass over the 3*M coefficients: dL/dsh[f] = b[f/3] dRGB[f%3] and
+      // dL/ddir += (db/ddir)[f/3] * sh[f] * dRGB[f%3].  16-byte loads/stores when 3*M % 4 == 0
+      // (M = 4, 16): a quarter of the L2 transactions of the per-float access pattern.
+      float ddx = 0.f, ddy = 0.f, ddz = 0.f;
+      const int nfl = a.M * 3;
+      if ((nfl & 3) == 0) {
+        const float4* __restrict__ sh4 = reinterpret_cast<const float4*>(a.shs + shbase);
+        float4* __restrict__ dsh4 = reinterpret_cast<float4*>(a.dL_dsh + shbase);
+#pragma unroll
+        for (int q = 0; q < 12; ++q) {
+          if (4 * q < nfl) {
+            const float4 v = __ldg(sh4 + q);
+            const float in[4] = {v.x, v.y, v.z, v.w};
+            float out[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int f = 4 * q + i, k = f / 3, ch = f % 3;
+              out[i] = b[k] * dRGB[ch];
+              const float t = in[i] * dRGB[ch];
+              ddx += bx[k] * t; ddy += by[k] * t; ddz += bz[k] * t;
+            }
+            dsh4[q] = make_float4(out[0], out[1], out[2], out[3]);
+          }
+        }
+      } else {
+        const float* __restrict__ sh = a.shs + shbase;
+        float* __restrict__ dsh = a.dL_dsh + shbase;
+#pragma unroll
+        for (int f = 0; f < 48; ++f) {
+          if (f < nfl) {
+            const int k = f / 3, ch = f % 3;
+            dsh[f] = b[k] * dRGB[ch];
+            const float t = __ldg(sh + f) * dRGB[ch];
+            ddx += bx[k] * t; ddy += by[k] * t; ddz += bz[k] * t;
+          }
         }
       }
-#undef SH
-#undef DSH
-      const float ddx = dRGBdx[0] * dRGB[0] + dRGBdx[1] * dRGB[1] + dRGBdx[2] * dRGB[2];
-      const float ddy = dRGBdy[0] * dRGB[0] + dRGBdy[1] * dRGB[1] + dRGBdy[2] * dRGB[2];
-      const float ddz = dRGBdz[0] * dRGB[0] + dRGBdz[1] * dRGB[1] + dRGBdz[2] * dRGB[2];
       // normalisation Jacobian (dnormvdv, auxiliary.h:95-112)
       const float sum2 = dox * dox + doy * doy + doz * doz;
       const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
@@ -314,8 +310,14 @@ preprocess_bwd_kernel(GcrPreprocessBwdArgs a) {
                 2.f * qy * (t[1][2] + t[2][1]) - 4.f * qz * (t[1][1] + t[0][0]);
     }
   } else if (kHasSH) {
-    float* __restrict__ dsh = a.dL_dsh + shbase;
-    for (int k = 0; k < a.M * 3; ++k) dsh[k] = 0.f;
+    const int nfl = a.M * 3;
+    if ((nfl & 3) == 0) {
+      float4* __restrict__ dsh4 = reinterpret_cast<float4*>(a.dL_dsh + shbase);
+      for (int q = 0; q < nfl / 4; ++q) dsh4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      float* __restrict__ dsh = a.dL_dsh + shbase;
+      for (int k = 0; k < nfl; ++k) dsh[k] = 0.f;
+    }
   }
 
   a.dL_dmean2D[3 * idx + 0] = o_m2x;

@@ -48,16 +48,24 @@ class _Allocator:
     """Resizable byte buffer handed to the library (resizeFunctional, rasterize_points.cu:27-33)."""
 
     def __init__(self, device):
-        self.device = device
         self.tensor = torch.empty(0, dtype=torch.uint8, device=device)
-        self.cb = _cabi.ALLOC_FN(self._alloc)
+        box = [self.tensor]   # the C callback closes over `box`, not over self: no reference
+        self._box = box       # cycle, so the (GB-sized) buffers die by refcount, not by GC
 
-    def _alloc(self, _ctx, nbytes):
-        try:
-            self.tensor = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
-            return self.tensor.data_ptr()
-        except Exception:  # surfaces as "allocation failed" from the library
-            return 0
+        def _alloc(_ctx, nbytes):
+            try:
+                box[0] = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+                return box[0].data_ptr()
+            except Exception:  # surfaces as "allocation failed" from the library
+                return 0
+        self.cb = _cabi.ALLOC_FN(_alloc)
+
+    def take(self):
+        """The buffer the library asked for (or the empty tensor); drops the callback."""
+        t = self._box[0]
+        self.cb = None
+        self._box = None
+        return t
 
 
 def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier,
@@ -100,7 +108,7 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
                 int(bool(prefiltered)), _ptr(out_color), _ptr(radii), int(bool(debug)),
                 int(shard_rank), int(shard_count), _stream_ptr(device))
             rendered = _cabi.check(rc, "rasterize_gaussians")
-    return rendered, out_color, radii, geom.tensor, binning.tensor, img.tensor
+    return rendered, out_color, radii, geom.take(), binning.take(), img.take()
 
 
 def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations,
