@@ -181,3 +181,67 @@ def mark_visible(means3D, viewmatrix, projmatrix):
                                                  _stream_ptr(device))
             _cabi.check(rc, "mark_visible")
     return present
+
+
+# ---- split backward for tile-sharded multi-GPU rendering (gaussiancity_b200.sharding) --------
+def rasterize_gaussians_backward_blend(background, P, R, dL_dout_color, binningBuffer, imageBuffer,
+                                       debug=False, shard_rank=0, shard_count=1):
+    """First half of the backward: per-tile gradient blend over this rank's tile rows.
+    -> grad_acc [P,12] fp32 (dmean2D.xy, dconic.xyw, dopacity, dcolor.rgb, 3 pad): PARTIAL sums
+    when shard_count > 1 (reduce across ranks before the geometry half)."""
+    lib = _cabi.lib()
+    device = dL_dout_color.device
+    H, W = int(dL_dout_color.size(1)), int(dL_dout_color.size(2))
+    with torch.cuda.device(device):
+        grad_acc = torch.empty((int(P), 12), dtype=torch.float32, device=device)
+        if P != 0:
+            background = _prep(background, "background", device)
+            dL_dout_color = _prep(dL_dout_color, "dL_dout_color", device)
+            rc = lib.gcr_rasterizer_backward_blend(
+                int(P), int(R), _ptr(background), W, H,
+                ctypes.c_void_p(binningBuffer.data_ptr()) if binningBuffer.numel() else None,
+                ctypes.c_void_p(imageBuffer.data_ptr()), _ptr(dL_dout_color), _ptr(grad_acc),
+                int(bool(debug)), int(shard_rank), int(shard_count), _stream_ptr(device))
+            _cabi.check(rc, "rasterize_gaussians_backward_blend")
+    return grad_acc
+
+
+def rasterize_gaussians_backward_geometry(means3D, radii, scales, rotations, scale_modifier,
+                                          cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy,
+                                          image_height, image_width, sh, degree, campos, geomBuffer,
+                                          grad_acc, range_start=0, range_count=-1, debug=False,
+                                          out=None):
+    """Second half of the backward: per-Gaussian geometry gradients for Gaussians
+    [range_start, range_start+range_count) from the (reduced) accumulator.  Returns the same
+    8-tuple as rasterize_gaussians_backward; rows outside the range are left untouched
+    (uninitialised unless `out` is supplied)."""
+    lib = _cabi.lib()
+    device = means3D.device
+    P = int(means3D.size(0))
+    M = int(sh.size(1)) if sh.numel() != 0 else 0
+    opts = dict(dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        if out is None:
+            out = (torch.empty((P, 3), **opts), torch.empty((P, 3), **opts), torch.empty((P, 1), **opts),
+                   torch.empty((P, 3), **opts), torch.empty((P, 6), **opts), torch.empty((P, M, 3), **opts),
+                   torch.empty((P, 3), **opts), torch.empty((P, 4), **opts))
+        dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drot = out
+        if P != 0:
+            means3D = _prep(means3D, "means3D", device)
+            scales = _prep(scales, "scales", device)
+            rotations = _prep(rotations, "rotations", device, align=16)
+            cov3D_precomp = _prep(cov3D_precomp, "cov3D_precomp", device)
+            viewmatrix = _prep(viewmatrix, "viewmatrix", device)
+            projmatrix = _prep(projmatrix, "projmatrix", device)
+            sh = _prep(sh, "sh", device, align=16)
+            campos = _prep(campos, "campos", device)
+            rc = lib.gcr_rasterizer_backward_geometry(
+                P, int(degree), M, _ptr(means3D), _ptr(sh), _ptr(scales), float(scale_modifier),
+                _ptr(rotations), _ptr(cov3D_precomp), _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos),
+                int(image_width), int(image_height), float(tan_fovx), float(tan_fovy),
+                _ptr(radii.contiguous()), ctypes.c_void_p(geomBuffer.data_ptr()), _ptr(grad_acc),
+                _ptr(dL_dmeans2D), None, _ptr(dL_dopacity), _ptr(dL_dcolors), _ptr(dL_dmeans3D),
+                _ptr(dL_dcov3D), _ptr(dL_dsh), _ptr(dL_dscales), _ptr(dL_drot), int(bool(debug)),
+                int(range_start), int(range_count), _stream_ptr(device))
+            _cabi.check(rc, "rasterize_gaussians_backward_geometry")
+    return out

@@ -58,6 +58,16 @@ static const real C3[7] = {(real)-0.5900435899266435f, (real)2.890611442640554f,
 
 int gso_is_double(void) { return GSO_DOUBLE; }
 
+/* Test-only "smooth" mode: removes the reference's discontinuities (alpha < 1/255 skip,
+ * T < 1e-4 stop, 3-sigma bounding square) so finite differences can validate the analytic
+ * backward formulas. Never used for parity. */
+static real g_alpha_min = (real)(1.0f / 255.0f), g_T_min = (real)0.0001f, g_radius_k = (real)3.0f;
+void gso_set_smooth(int on) {
+  g_alpha_min = on ? (real)0 : (real)(1.0f / 255.0f);
+  g_T_min = on ? (real)0 : (real)0.0001f;
+  g_radius_k = on ? (real)12.0f : (real)3.0f;
+}
+
 /* column-major 3x3 helpers: m[c][r], product as glm::operator*(mat3,mat3) */
 typedef struct { real m[3][3]; } M3;
 static M3 m3mul(const M3* A, const M3* B) {
@@ -182,7 +192,7 @@ long gso_preprocess(int P, int D, int M, int W, int H, const float* means3D, con
     const real mid = (real)0.5f * (cv.a + cv.c);
     const real sq = R_SQRT(R_FMAX((real)0.1f, mid * mid - det));
     const real l1 = mid + sq, l2 = mid - sq;
-    const real rad = R_CEIL((real)3.0f * R_SQRT(R_FMAX(l1, l2)));
+    const real rad = R_CEIL(g_radius_k * R_SQRT(R_FMAX(l1, l2)));
     const real pxi = ndc2pix(ndcx, W), pyi = ndc2pix(ndcy, H);
     int x0, y0, x1, y1;
     get_rect(pxi, pyi, (int)rad, gx, gy, &x0, &y0, &x1, &y1);
@@ -293,9 +303,9 @@ void gso_render(int W, int H, const uint32_t* ranges, const uint32_t* point_list
           const real power = (real)-0.5f * (co[0] * dx * dx + co[2] * dy * dy) - co[1] * dx * dy;
           if (power > 0) continue;
           const real alpha = R_FMIN((real)0.99f, co[3] * R_EXP(power));
-          if (alpha < (real)(1.0f / 255.0f)) continue;
+          if (alpha < g_alpha_min) continue;
           const real test_T = T * (1 - alpha);
-          if (test_T < (real)0.0001f) break;
+          if (test_T < g_T_min) break;
           for (int ch = 0; ch < 3; ++ch) C[ch] += colors[3 * (size_t)g + ch] * alpha * T;
           T = test_T; last = contributor;
         }
@@ -339,7 +349,7 @@ void gso_render_backward(int W, int H, const uint32_t* ranges, const uint32_t* p
           if (power > 0) continue;
           const real G = R_EXP(power);
           const real alpha = R_FMIN((real)0.99f, co[3] * G);
-          if (alpha < (real)(1.0f / 255.0f)) continue;
+          if (alpha < g_alpha_min) continue;
           T = T / (1 - alpha);
           const real dchannel_dcolor = alpha * T;
           real dL_dalpha = 0;

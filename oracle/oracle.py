@@ -57,6 +57,11 @@ class OracleResult:
     pass
 
 
+def set_smooth(on, precision="f64"):
+    """Test-only: drop the alpha/T thresholds and widen the bounding square (see gs_oracle.c)."""
+    _lib(precision).gso_set_smooth(1 if on else 0)
+
+
 def forward(means3D, opacities, scales, rotations, view_matrix, proj_matrix, campos, img_w, img_h,
             tanfovx, tanfovy, bg, shs=None, colors_precomp=None, sh_degree=0, scale_modifier=1.0,
             cov3D_precomp=None, precision="f32"):
@@ -110,23 +115,35 @@ def forward(means3D, opacities, scales, rotations, view_matrix, proj_matrix, cam
     return r
 
 
-def backward(r, dL_dpix):
-    """Gradients for an OracleResult. Returns dict with the reference's 8 output tensors
-    (+ dL_dconic [P,3] = (x,y,w))."""
+def backward_blend(r, dL_dpix):
+    """Per-tile gradient blend only (backward.cu:428-581): dict with dL_dmean2D [P,2],
+    dL_dconic [P,3] (x,y,w), dL_dopacity [P,1], dL_dcolor [P,3]."""
     l = _lib(r.precision)
     real = np.float32 if r.precision == "f32" else np.float64
-    P, W, H, M = r.P, r.W, r.H, r.M
+    P, W, H = r.P, r.W, r.H
     i = r.inputs
     dL_dpix = np.ascontiguousarray(np.asarray(dL_dpix, dtype=real))
     g = dict(dL_dmean2D=np.zeros((P, 2), real), dL_dconic=np.zeros((P, 3), real),
-             dL_dopacity=np.zeros((P, 1), real), dL_dcolor=np.zeros((P, 3), real),
-             dL_dmean3D=np.zeros((P, 3), real), dL_dcov3D=np.zeros((P, 6), real),
-             dL_dsh=np.zeros((P, M, 3), real), dL_dscale=np.zeros((P, 3), real),
-             dL_drot=np.zeros((P, 4), real))
+             dL_dopacity=np.zeros((P, 1), real), dL_dcolor=np.zeros((P, 3), real))
     l.gso_render_backward(W, H, _p(r.ranges), _p(r._pl_buf), _p(i["bg"]), _p(r.means2D),
                           _p(r.conic_opacity), _p(r.colors), _p(r.final_T), _p(r.n_contrib),
                           _p(dL_dpix), _p(g["dL_dmean2D"]), _p(g["dL_dconic"]), _p(g["dL_dopacity"]),
                           _p(g["dL_dcolor"]))
+    return g
+
+
+def backward_geometry(r, blend):
+    """Per-Gaussian geometry backward (backward.cu:143-293, 378-425) from backward_blend()'s
+    (possibly cross-rank reduced) output. Returns the remaining gradient arrays."""
+    l = _lib(r.precision)
+    real = np.float32 if r.precision == "f32" else np.float64
+    P, W, H, M = r.P, r.W, r.H, r.M
+    i = r.inputs
+    c = lambda a: np.ascontiguousarray(np.asarray(a, dtype=real))
+    d2, dc, dcol = c(blend["dL_dmean2D"]), c(blend["dL_dconic"]), c(blend["dL_dcolor"])
+    g = dict(dL_dmean3D=np.zeros((P, 3), real), dL_dcov3D=np.zeros((P, 6), real),
+             dL_dsh=np.zeros((P, M, 3), real), dL_dscale=np.zeros((P, 3), real),
+             dL_drot=np.zeros((P, 4), real))
     has_sh = i["shs"] is not None
     has_scale = i["scales"] is not None and i["cov3D_precomp"] is None
     l.gso_geometry_backward(P, r.D, M, W, H, _p(i["means3D"]), _p(r.radii), _p(i["shs"]),
@@ -134,11 +151,19 @@ def backward(r, dL_dpix):
                             _p(i["rotations"]) if has_scale else None,
                             ctypes.c_float(i["scale_modifier"]), _p(i["cov3D_precomp"]), _p(i["V"]),
                             _p(i["PM"]), _p(i["campos"]), ctypes.c_float(i["tanfovx"]),
-                            ctypes.c_float(i["tanfovy"]), _p(g["dL_dmean2D"]), _p(g["dL_dconic"]),
-                            _p(g["dL_dcolor"]), _p(g["dL_dmean3D"]), _p(g["dL_dcov3D"]),
+                            ctypes.c_float(i["tanfovy"]), _p(d2), _p(dc), _p(dcol),
+                            _p(g["dL_dmean3D"]), _p(g["dL_dcov3D"]),
                             _p(g["dL_dsh"]) if has_sh else None,
                             _p(g["dL_dscale"]) if has_scale else None,
                             _p(g["dL_drot"]) if has_scale else None)
+    return g
+
+
+def backward(r, dL_dpix):
+    """Gradients for an OracleResult. Returns dict with the reference's 8 output tensors
+    (+ dL_dconic [P,3] = (x,y,w))."""
+    g = backward_blend(r, dL_dpix)
+    g.update(backward_geometry(r, g))
     return g
 
 

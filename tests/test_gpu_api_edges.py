@@ -1,0 +1,136 @@
+"""GPU: public operator surface (autograd Function, nn.Module, camera wrapper) and the edge
+cases the reference boundary handles: empty input, everything culled, degenerate sizes."""
+import numpy as np
+import pytest
+import torch
+
+import gaussiancity_b200 as g
+from gaussiancity_b200 import ext as ours
+from gaussiancity_b200.synthetic import CITY_K, CITY_SENSOR, city_points, uniform_scene
+from oracle import oracle
+
+from . import refext
+
+pytestmark = pytest.mark.gpu
+
+
+def _settings(s, **kw):
+    d = dict(img_h=s.img_h, img_w=s.img_w, tanfovx=s.tanfovx, tanfovy=s.tanfovy, bg=s.bg, scale_modifier=1.0,
+             view_matrix=s.view_matrix, proj_matrix=s.proj_matrix, sh_degree=s.sh_degree, campos=s.campos,
+             prefiltered=False, debug=False)
+    d.update(kw)
+    return g.GaussianRasterizationSettings(**d)
+
+
+def test_autograd_surface_matches_oracle(built_lib, cuda_device):
+    s = uniform_scene(1500, 128, 96, sh_degree=2, seed=3, device=cuda_device)
+    leaves = [t.clone().requires_grad_(True) for t in (s.means3D, s.shs, s.opacities, s.scales, s.rotations)]
+    m3, sh, op, sc, ro = leaves
+    m2 = torch.zeros_like(m3, requires_grad=True)
+    color, radii = g.GaussianRasterizer(_settings(s))(m3, m2, op, shs=sh, scales=sc, rotations=ro)
+    assert color.shape == (3, 96, 128) and radii.dtype == torch.int32 and not radii.requires_grad
+    G = torch.randn(3, 96, 128, generator=torch.Generator().manual_seed(8)).to(cuda_device)
+    (color * G).sum().backward()
+    r = oracle.forward_scene(s, "f64")
+    gb = oracle.backward(r, G.cpu().numpy().astype(np.float64))
+    rel = lambda a, b: np.linalg.norm(a.detach().cpu().numpy() - b) / max(np.linalg.norm(b), 1e-30)
+    assert rel(m3.grad, gb["dL_dmean3D"]) < 1e-4 and rel(sh.grad, gb["dL_dsh"]) < 1e-4
+    assert rel(op.grad, gb["dL_dopacity"]) < 1e-4 and rel(sc.grad, gb["dL_dscale"]) < 1e-4
+    assert rel(ro.grad, gb["dL_drot"]) < 1e-4 and rel(m2.grad[:, :2], gb["dL_dmean2D"]) < 1e-4
+    assert bool((m2.grad[:, 2] == 0).all())
+
+
+def test_debug_mode_and_cov3d_precomp_path(built_lib, cuda_device):
+    s = uniform_scene(800, 96, 96, sh_degree=0, seed=5, device=cuda_device, use_sh=False)
+    r = oracle.forward_scene(s, "f32")
+    cov = torch.from_numpy(r.cov3D.astype(np.float32)).to(cuda_device).requires_grad_(True)
+    col = s.colors_precomp.clone().requires_grad_(True)
+    color, radii = g.GaussianRasterizer(_settings(s, debug=True))(
+        s.means3D, torch.zeros_like(s.means3D), s.opacities, colors_precomp=col, cov3D_precomp=cov)
+    assert np.allclose(color.detach().cpu().numpy(), r.color, rtol=1e-3, atol=2e-4)
+    color.sum().backward()
+    gb = oracle.backward(r, np.ones((3, 96, 96), np.float32))
+    assert np.linalg.norm(cov.grad.cpu().numpy() - gb["dL_dcov3D"]) <= 1e-3 * np.linalg.norm(gb["dL_dcov3D"])
+    assert np.linalg.norm(col.grad.cpu().numpy() - gb["dL_dcolor"]) <= 1e-4 * np.linalg.norm(gb["dL_dcolor"])
+
+
+def test_wrapper_city_frame_matches_reference_and_oracle(built_lib, cuda_device):
+    """GaussianCity call pattern: [N,14] points, K / sensor camera, negative clip-space w, flips."""
+    pts, cam_pos, cam_quat = city_points(40_000, seed=2, device=cuda_device)
+    wrap = g.GaussianRasterizerWrapper(CITY_K, CITY_SENSOR, device=cuda_device)
+    img = wrap(pts, cam_pos, cam_quat)
+    assert img.shape == (3, 540, 960) and torch.isfinite(img).all() and img.abs().sum() > 0
+    st = wrap._get_gaussian_rasterization_settings(cam_pos, cam_quat)
+    r = oracle.forward(pts[:, 0:3].cpu().numpy(), pts[:, 3:4].cpu().numpy(), pts[:, 4:7].cpu().numpy(),
+                       pts[:, 7:11].cpu().numpy(), st.view_matrix.cpu().numpy(), st.proj_matrix.cpu().numpy(),
+                       st.campos.cpu().numpy(), 960, 540, st.tanfovx, st.tanfovy, st.bg.cpu().numpy(),
+                       colors_precomp=pts[:, 11:14].cpu().numpy(), precision="f32")
+    assert (r.radii > 0).sum() > 1000
+    assert np.allclose(torch.flip(img, dims=[2]).cpu().numpy(), r.color, rtol=1e-3, atol=5e-4)
+    ref = refext.load_reference_ext()
+    if ref is not None:
+        e = torch.Tensor([])
+        _, col_ref, rad_ref, *_ = ref.rasterize_gaussians(
+            st.bg, pts[:, 0:3].contiguous(), pts[:, 11:14].contiguous(), pts[:, 3:4].contiguous(),
+            pts[:, 4:7].contiguous(), pts[:, 7:11].contiguous(), 1.0, e, st.view_matrix, st.proj_matrix,
+            st.tanfovx, st.tanfovy, 540, 960, e, 0, st.campos, False, False)
+        assert torch.equal(torch.flip(img, dims=[2]), col_ref)     # precomputed colours: bit-exact
+
+
+def test_empty_and_fully_culled_inputs(built_lib, cuda_device):
+    s = uniform_scene(64, 48, 40, seed=1, device=cuda_device, bg=(0.5, 0.25, 0.125))
+    e = torch.Tensor([])
+    # P == 0: zeros, no launch (rasterize_points.cu:71)
+    out = ours.rasterize_gaussians(s.bg, torch.zeros(0, 3, device=cuda_device), e, torch.zeros(0, 1, device=cuda_device),
+                                   torch.zeros(0, 3, device=cuda_device), torch.zeros(0, 4, device=cuda_device), 1.0, e,
+                                   s.view_matrix, s.proj_matrix, s.tanfovx, s.tanfovy, 40, 48,
+                                   torch.zeros(0, 1, 3, device=cuda_device), 0, s.campos, False, False)
+    assert out[0] == 0 and out[1].shape == (3, 40, 48) and bool((out[1] == 0).all()) and out[2].numel() == 0
+    # everything behind the camera: R == 0, image == background, zero gradients
+    behind = s._replace(means3D=s.means3D * torch.tensor([1.0, 1.0, -1.0], device=cuda_device))
+    R, color, radii, geom, binning, img = ours.rasterize_gaussians(*refext.scene_forward_args(behind))
+    assert R == 0 and bool((radii == 0).all())
+    assert torch.equal(color, s.bg[:, None, None].expand(3, 40, 48))
+    grads = ours.rasterize_gaussians_backward(*refext.scene_backward_args(behind, radii, torch.ones_like(color), geom, R, binning, img))
+    assert all(bool((t == 0).all()) for t in grads)
+    assert not bool(ours.mark_visible(behind.means3D, s.view_matrix, s.proj_matrix).any())
+
+
+@pytest.mark.parametrize("W,H", [(1, 1), (16, 16), (17, 15), (250, 3)])
+def test_degenerate_image_sizes(built_lib, cuda_device, W, H):
+    s = uniform_scene(500, W, H, sh_degree=1, seed=6, device=cuda_device, sigma_px=(0.5, 30.0))
+    R, color, radii, geom, binning, img = ours.rasterize_gaussians(*refext.scene_forward_args(s))
+    r = oracle.forward_scene(s, "f32")
+    assert (radii.cpu().numpy() != r.radii).sum() <= 1
+    assert np.allclose(color.cpu().numpy(), r.color, rtol=1e-3, atol=3e-4)
+
+
+def test_long_tile_lists_and_saturation(built_lib, cuda_device):
+    """Thousands of large, opaque splats on a small image: lists far longer than one TMA batch,
+    every pixel saturates (T < 1e-4) long before its list ends."""
+    s = uniform_scene(6000, 64, 48, sh_degree=0, seed=12, device=cuda_device, sigma_px=(6.0, 20.0))
+    s = s._replace(opacities=torch.full_like(s.opacities, 0.95))
+    G = torch.ones(3, 48, 64, device=cuda_device)
+    R, color, radii, geom, binning, img = ours.rasterize_gaussians(*refext.scene_forward_args(s))
+    grads = ours.rasterize_gaussians_backward(*refext.scene_backward_args(s, radii, G, geom, R, binning, img))
+    assert R / 12 > 1000          # mean list length per tile
+    r = oracle.forward_scene(s, "f32")
+    gb = oracle.backward(r, G.cpu().numpy())
+    assert np.allclose(color.cpu().numpy(), r.color, rtol=1e-3, atol=3e-4)
+    ov = refext.our_views(6000, R, 64, 48, geom, binning, img)
+    assert (ov["n_contrib"].cpu().numpy() != r.n_contrib.astype(np.int32)).mean() < 5e-3
+    assert float(ov["final_T"].max()) < 1e-2
+    for a, name in [(grads[3], "dL_dmean3D"), (grads[2], "dL_dopacity"), (grads[6], "dL_dscale")]:
+        assert np.linalg.norm(a.cpu().numpy() - gb[name]) <= 2e-3 * np.linalg.norm(gb[name]), name
+
+
+def test_non_contiguous_and_offset_inputs(built_lib, cuda_device):
+    """[N,14] slices as utils/helpers.get_gaussian_points hands them over (strided views)."""
+    s = uniform_scene(2000, 96, 64, seed=14, device=cuda_device, use_sh=False)
+    packed = torch.cat([s.means3D, s.opacities, s.scales, s.rotations, s.colors_precomp], dim=1)
+    e = torch.Tensor([])
+    a = ours.rasterize_gaussians(s.bg, packed[:, 0:3], packed[:, 11:14], packed[:, 3:4], packed[:, 4:7],
+                                 packed[:, 7:11], 1.0, e, s.view_matrix, s.proj_matrix, s.tanfovx, s.tanfovy,
+                                 64, 96, e, 0, s.campos, False, False)
+    b = ours.rasterize_gaussians(*refext.scene_forward_args(s))
+    assert a[0] == b[0] and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])

@@ -1,0 +1,209 @@
+"""GPU: the CUDA path (through the C ABI) against the CPU oracle and the committed golden
+fixtures on seeded inputs, plus size-independent properties at BASELINE's full sizes.
+Bars: bit-exact integer / index work; <= 1e-4 relative on colours and gradients."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from gaussiancity_b200 import ext as ours
+from gaussiancity_b200.synthetic import Scene, uniform_scene
+from oracle import oracle
+
+from . import refext
+
+pytestmark = pytest.mark.gpu
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    den = np.linalg.norm(b)
+    return float(np.linalg.norm(a - b) / (den if den > 0 else 1.0))
+
+
+def scene_from_golden(d, dev):
+    t = lambda k: torch.from_numpy(d[k]).to(dev) if k in d else None
+    return Scene(t("means3D"), t("scales"), t("rotations"), t("opacities"), t("shs"), t("colors_precomp"),
+                 int(d["sh_degree"]), int(d["img_w"]), int(d["img_h"]), float(d["tanfovx"]),
+                 float(d["tanfovy"]), t("view_matrix"), t("proj_matrix"), t("campos"), t("bg"))
+
+
+def run_ours(s, grad_out=None, **kw):
+    out = ours.rasterize_gaussians(*refext.scene_forward_args(s), **kw)
+    R, color, radii, geom, binning, img = out
+    grads = None
+    if grad_out is not None:
+        grads = ours.rasterize_gaussians_backward(
+            *refext.scene_backward_args(s, radii, grad_out, geom, R, binning, img), **kw)
+    torch.cuda.synchronize()
+    return out, grads
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_cuda_matches_reference_golden(built_lib, cuda_device, path):
+    """Golden vectors were produced by the unmodified reference on a B200: everything the
+    arithmetic pins must be bit-identical, including the negative-w GaussianCity camera."""
+    d = np.load(path)
+    s = scene_from_golden(d, cuda_device)
+    G = torch.from_numpy(d["grad_out"]).to(cuda_device)
+    (R, color, radii, geom, binning, img), grads = run_ours(s, G)
+    P, W, H = s.means3D.shape[0], s.img_w, s.img_h
+    ov = refext.our_views(P, R, W, H, geom, binning, img)
+    assert R == int(d["num_rendered"])
+    assert np.array_equal(radii.cpu().numpy(), d["radii"])
+    assert np.array_equal(ov["tiles_touched"].cpu().numpy(), d["tiles_touched"])
+    assert np.array_equal(ov["point_list"].cpu().numpy(), d["point_list"])
+    assert np.array_equal(ov["ranges"].cpu().numpy(), d["ranges"])
+    assert np.array_equal(ov["n_contrib"].cpu().numpy(), d["n_contrib"])
+    assert np.array_equal(ov["final_T"].cpu().numpy(), d["final_T"])
+    vis = d["radii"] > 0
+    rec = ov["records"].cpu().numpy()
+    assert np.array_equal(rec[vis][:, 0:2], d["means2D"][vis])
+    assert np.array_equal(np.concatenate([rec[vis][:, 2:4], rec[vis][:, 4:6]], 1), d["conic_opacity"][vis])
+    assert np.allclose(color.cpu().numpy(), d["color"], rtol=1e-4, atol=1e-6)
+    names = ["dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dcov3D", "dL_dsh", "dL_dscales", "dL_drotations"]
+    for n, g in zip(names, grads):
+        if d[n].size:
+            assert rel(g.cpu().numpy(), d[n]) < 1e-4, n
+
+
+@pytest.mark.parametrize("P,W,H,deg,use_sh,seed", [
+    (3000, 200, 120, 3, True, 41), (20000, 320, 256, 0, False, 42), (50, 33, 17, 2, True, 43)])
+def test_cuda_matches_cpu_oracle(built_lib, cuda_device, P, W, H, deg, use_sh, seed):
+    s = uniform_scene(P, W, H, sh_degree=deg, seed=seed, device=cuda_device, use_sh=use_sh, bg=(0.3, 0.1, 0.5))
+    G = torch.randn(3, H, W, generator=torch.Generator().manual_seed(seed)).to(cuda_device)
+    (R, color, radii, geom, binning, img), grads = run_ours(s, G)
+    r = oracle.forward_scene(s, "f32")
+    g = oracle.backward(r, G.cpu().numpy())
+    # CPU fp32 has no FMA: a ceil() may flip on a handful of Gaussians; when none does, every
+    # index array must agree exactly
+    nflip = int((radii.cpu().numpy() != r.radii).sum())
+    assert nflip <= max(1, P // 20000)
+    if nflip == 0:
+        ov = refext.our_views(P, R, W, H, geom, binning, img)
+        assert R == r.num_rendered
+        pl, opl = ov["point_list"].cpu().numpy(), r.point_list.astype(np.int32)
+        # depth ties broken identically; FMA-vs-no-FMA depth differences can swap near-equal depths
+        assert (pl != opl).mean() < 1e-3
+        assert np.array_equal(ov["ranges"].cpu().numpy(), r.ranges.astype(np.int32))
+        assert (ov["n_contrib"].cpu().numpy() != r.n_contrib.astype(np.int32)).mean() < 1e-3
+    assert np.allclose(color.cpu().numpy(), r.color, rtol=1e-3, atol=2e-4)
+    pairs = [("dL_dmean2D", grads[0][:, :2]), ("dL_dcolor", grads[1]), ("dL_dopacity", grads[2]),
+             ("dL_dmean3D", grads[3]), ("dL_dcov3D", grads[4]), ("dL_dsh", grads[5]),
+             ("dL_dscale", grads[6]), ("dL_drot", grads[7])]
+    for name, t in pairs:
+        if t.numel() and (name != "dL_dsh" or use_sh):
+            assert rel(t.cpu().numpy(), g[name]) < 5e-4, name
+
+
+# ---- properties at BASELINE's full sizes (config 3: 1 M Gaussians, SH 3, 1920x1080) ---------------
+@pytest.fixture(scope="module")
+def big(built_lib, cuda_device):
+    s = uniform_scene(1_000_000, 1920, 1080, sh_degree=3, seed=77, device=cuda_device)
+    G = torch.randn(3, 1080, 1920, generator=torch.Generator().manual_seed(1)).to(cuda_device)
+    out, grads = run_ours(s, G)
+    return s, G, out, grads
+
+
+def test_full_size_binning_invariants(big):
+    s, G, (R, color, radii, geom, binning, img), grads = big
+    P, W, H = s.means3D.shape[0], s.img_w, s.img_h
+    ov = refext.our_views(P, R, W, H, geom, binning, img)
+    assert int(ov["tiles_touched"].long().sum()) == R                     # checksum of counts
+    assert int(ov["offsets"][-1]) == R
+    keys = ov["tile_keys"].long()
+    assert bool((keys[1:] >= keys[:-1]).all())                            # sorted by tile
+    # within a tile: depth ascending, ties by ascending Gaussian index (stable sort semantics)
+    depth = torch.full((P,), float("inf"), device=radii.device)
+    vis = radii > 0
+    sg = ov["sorted_gauss"].long()
+    sk = ov["sorted_depth_keys"].view(torch.float32)
+    depth[sg] = sk
+    pl = ov["point_list"].long()
+    same = keys[1:] == keys[:-1]
+    d0, d1 = depth[pl[:-1]], depth[pl[1:]]
+    assert bool((~same | (d1 > d0) | ((d1 == d0) & (pl[1:] > pl[:-1]))).all())
+    # ranges partition [0, R) and agree with the keys
+    rg = ov["ranges"].long()
+    nonempty = rg[:, 1] > rg[:, 0]
+    assert int((rg[:, 1] - rg[:, 0]).sum()) == R
+    t_ids = torch.nonzero(nonempty).flatten()
+    assert bool((keys[rg[t_ids, 0]] == t_ids).all()) and bool((keys[rg[t_ids, 1] - 1] == t_ids).all())
+    assert bool((rg[~nonempty] == 0).all())
+    # every culled Gaussian: radius 0, no tiles; every visible one: in front of the near plane
+    assert bool((ov["tiles_touched"][~vis] == 0).all())
+    assert bool((s.means3D[vis][:, 2] > 0.2).all())
+    # n_contrib never exceeds the tile's list length
+    nc = ov["n_contrib"].long()
+    tile_of_pix = (torch.arange(H, device=nc.device)[:, None] // 16) * ((W + 15) // 16) + torch.arange(W, device=nc.device)[None, :] // 16
+    assert bool((nc <= (rg[:, 1] - rg[:, 0])[tile_of_pix]).all())
+    ft = ov["final_T"]
+    assert bool(((ft > 0) & (ft <= 1)).all()) and torch.isfinite(color).all()
+
+
+def test_full_size_forward_is_deterministic(big):
+    s, G, (R, color, radii, geom, binning, img), grads = big
+    (R2, color2, radii2, geom2, binning2, img2), _ = run_ours(s)
+    assert R2 == R and torch.equal(color, color2) and torch.equal(radii, radii2)
+    P, W, H = s.means3D.shape[0], s.img_w, s.img_h
+    a, b = refext.our_views(P, R, W, H, geom, binning, img), refext.our_views(P, R, W, H, geom2, binning2, img2)
+    for k in ("point_list", "ranges", "n_contrib", "final_T"):
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_full_size_backward_is_linear_in_upstream_gradient(big):
+    s, G, (R, color, radii, geom, binning, img), grads = big
+    G2 = torch.randn_like(G)
+    g2 = ours.rasterize_gaussians_backward(*refext.scene_backward_args(s, radii, G2, geom, R, binning, img))
+    g12 = ours.rasterize_gaussians_backward(*refext.scene_backward_args(s, radii, 2.0 * G + G2, geom, R, binning, img))
+    for a, b, c in zip(grads, g2, g12):
+        if a.numel():
+            lin = 2.0 * a.double() + b.double()
+            assert (c.double() - lin).norm().item() <= 2e-5 * lin.norm().item()
+
+
+def test_full_size_background_enters_linearly(big, cuda_device):
+    s, G, (R, color, radii, geom, binning, img), grads = big
+    P, W, H = s.means3D.shape[0], s.img_w, s.img_h
+    ft = refext.our_views(P, R, W, H, geom, binning, img)["final_T"]
+    bg = torch.tensor([0.25, 0.5, 1.0], device=cuda_device)
+    (R2, color2, *_), _ = run_ours(s._replace(bg=bg))
+    assert R2 == R
+    assert torch.allclose(color2, color + ft[None] * bg[:, None, None], rtol=0, atol=1e-6)
+
+
+def test_tile_row_shards_partition_the_frame(big):
+    """shard_count = 3 on one GPU, ranks run one after the other: image rows are disjoint and
+    their union is the single-GPU frame bit for bit; partial accumulators sum to the full one."""
+    s, G, (R, color, radii, geom, binning, img), grads = big
+    P, H = s.means3D.shape[0], s.img_h
+    total, Rsum = torch.zeros_like(color), 0
+    acc = torch.zeros(P, 12, device=color.device, dtype=torch.float64)
+    for k in range(3):
+        (Rk, ck, rk, gk, bk, ik), _ = run_ours(s, shard_rank=k, shard_count=3)
+        assert torch.equal(rk, radii)
+        rows = torch.zeros(H, dtype=torch.bool, device=color.device)
+        for r in range(k, (H + 15) // 16, 3):
+            rows[r * 16:(r + 1) * 16] = True
+        assert bool((ck[:, ~rows] == 0).all())
+        total += ck
+        Rsum += Rk
+        acc += ours.rasterize_gaussians_backward_blend(s.bg, P, Rk, G, bk, ik, shard_rank=k, shard_count=3).double()
+    assert Rsum == R and torch.equal(total, color)
+    full = ours.rasterize_gaussians_backward_blend(s.bg, P, R, G, binning, img).double()
+    assert (acc - full)[:, :9].norm().item() <= 1e-5 * full[:, :9].norm().item()
+    # finishing the geometry backward per slice reproduces the monolithic backward
+    e = torch.Tensor([])
+    out = None
+    third = (P + 2) // 3
+    for k in range(3):
+        st, cnt = k * third, max(0, min(P, (k + 1) * third) - k * third)
+        out = ours.rasterize_gaussians_backward_geometry(
+            s.means3D, radii, s.scales, s.rotations, 1.0, e, s.view_matrix, s.proj_matrix, s.tanfovx,
+            s.tanfovy, s.img_h, s.img_w, s.shs, s.sh_degree, s.campos, geom, full.float(),
+            range_start=st, range_count=cnt, out=out)
+    for a, b in zip(out, grads):
+        assert (a.double() - b.double()).norm().item() <= 1e-5 * max(b.double().norm().item(), 1e-30)

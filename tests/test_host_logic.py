@@ -1,0 +1,112 @@
+"""CPU: host-side mirror of the reference operator surface (DGR/__init__.py) -- argument
+validation, settings tuple, camera adapter math, refusal to run without CUDA."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import gaussiancity_b200 as g
+from gaussiancity_b200.synthetic import CITY_K, CITY_SENSOR, city_points, uniform_scene
+
+
+def test_settings_fields_match_reference_order():
+    assert g.GaussianRasterizationSettings._fields == (
+        "img_h", "img_w", "tanfovx", "tanfovy", "bg", "scale_modifier", "view_matrix", "proj_matrix",
+        "sh_degree", "campos", "prefiltered", "debug")
+
+
+def _settings(s):
+    return g.GaussianRasterizationSettings(s.img_h, s.img_w, s.tanfovx, s.tanfovy, s.bg, 1.0,
+                                           s.view_matrix, s.proj_matrix, s.sh_degree, s.campos, False, False)
+
+
+def test_rasterizer_argument_validation():
+    s = uniform_scene(10, 32, 32, seed=0)
+    r = g.GaussianRasterizer(_settings(s))
+    m2 = torch.zeros_like(s.means3D)
+    with pytest.raises(Exception, match="SHs or precomputed colors"):
+        r(s.means3D, m2, s.opacities, shs=None, colors_precomp=None, scales=s.scales, rotations=s.rotations)
+    with pytest.raises(Exception, match="SHs or precomputed colors"):
+        r(s.means3D, m2, s.opacities, shs=s.shs, colors_precomp=torch.zeros(10, 3), scales=s.scales,
+          rotations=s.rotations)
+    with pytest.raises(Exception, match="scale/rotation pair or precomputed 3D covariance"):
+        r(s.means3D, m2, s.opacities, shs=s.shs, scales=s.scales, rotations=None)
+    with pytest.raises(Exception, match="scale/rotation pair or precomputed 3D covariance"):
+        r(s.means3D, m2, s.opacities, shs=s.shs, scales=s.scales, rotations=s.rotations,
+          cov3D_precomp=torch.zeros(10, 6))
+
+
+def test_cpu_tensors_are_refused_not_silently_computed(built_lib):
+    s = uniform_scene(10, 32, 32, seed=0)
+    r = g.GaussianRasterizer(_settings(s))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        r(s.means3D, torch.zeros_like(s.means3D), s.opacities, shs=s.shs, scales=s.scales,
+          rotations=s.rotations)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        g.mark_visible(s.means3D, s.view_matrix, s.proj_matrix)
+
+
+def test_bad_means_shape_raises(built_lib):
+    from gaussiancity_b200 import ext
+    e = torch.Tensor([])
+    with pytest.raises(RuntimeError, match=r"means3D must have dimensions \(num_points, 3\)"):
+        ext.rasterize_gaussians(torch.zeros(3), torch.zeros(5, 4), e, torch.zeros(5, 1), e, e, 1.0, e,
+                                torch.eye(4), torch.eye(4), 1.0, 1.0, 8, 8, e, 0, torch.zeros(3), False, False)
+
+
+def test_wrapper_camera_matches_reference_formulas():
+    """fov / projection / w2c as DGR/__init__.py:326-402 computes them (restated here)."""
+    w = g.GaussianRasterizerWrapper(CITY_K, CITY_SENSOR, device=torch.device("cpu"))
+    fx, fy, cx, cy = CITY_K[0, 0], CITY_K[1, 1], CITY_K[0, 2], CITY_K[1, 2]
+    assert w.fov_x == pytest.approx(2 * math.atan2(960, 2 * fx))
+    assert w.fov_y == pytest.approx(2 * math.atan2(540, 2 * fy))
+    P = w.P.numpy()
+    zn, zf = 0.01, 50000.0
+    exp = np.zeros((4, 4), np.float32)
+    exp[0, 0], exp[1, 1] = 2 * fx / 960, 2 * fy / 540
+    exp[0, 2], exp[1, 2] = 2 * cx / 960 - 1, 2 * cy / 540 - 1
+    exp[2, 2], exp[3, 2], exp[2, 3] = -(zf + zn) / (zf - zn), -1.0, -2 * zf * zn / (zf - zn)
+    assert np.array_equal(P, exp)
+    _, cam_pos, cam_quat = city_points(10, seed=1)
+    st = w._get_gaussian_rasterization_settings(cam_pos, cam_quat)
+    assert (st.img_w, st.img_h) == CITY_SENSOR and st.sh_degree == 0 and st.scale_modifier == 1.0
+    w2c = st.view_matrix.T.numpy().astype(np.float64)
+    R = w2c[:3, :3]
+    assert np.allclose(R @ R.T, np.eye(3), atol=1e-6)          # rigid
+    assert np.allclose(w2c[:3, :3] @ cam_pos + w2c[:3, 3], 0, atol=1e-3)  # camera centre -> origin
+    assert np.allclose(st.campos.numpy(), cam_pos, atol=1e-2)
+    assert torch.allclose(st.proj_matrix, st.view_matrix @ w.P.T)
+    # the scene centre is in front of the camera (z_view > 0.2) and has NEGATIVE clip w
+    p = np.array([0.0, 0.0, 10.0, 1.0])
+    assert (w2c @ p)[2] > 0.2
+    assert (st.proj_matrix.T.numpy().astype(np.float64) @ p)[3] < 0
+
+
+def test_wrapper_requires_14_channels():
+    w = g.GaussianRasterizerWrapper(CITY_K, CITY_SENSOR, device=torch.device("cpu"))
+    with pytest.raises(AssertionError, match="14 channels"):
+        w(torch.zeros(5, 13), np.zeros(3), np.array([0, 0, 0, 1.0]))
+
+
+def test_compat_module_exports_reference_names(built_lib):
+    import importlib
+    import os
+    import sys
+    d = os.path.join(os.path.dirname(g.__file__), "compat")
+    sys.path.insert(0, d)
+    try:
+        m = importlib.import_module("diff_gaussian_rasterization_ext")
+        for n in ("rasterize_gaussians", "rasterize_gaussians_backward", "mark_visible"):
+            assert callable(getattr(m, n))
+    finally:
+        sys.path.remove(d)
+        sys.modules.pop("diff_gaussian_rasterization_ext", None)
+
+
+def test_bench_kernel_count_formula():
+    import bench
+    # 1080p: 8160 tiles -> 13 bits -> 2 tile passes; 1 + 12 + 3 + 1 + 6 + 1 + 1 (+2 backward)
+    assert bench.tile_sort_passes(1920, 1080) == 2
+    assert bench.kernels_per_step(1920, 1080) == 27
+    assert bench.tile_sort_passes(128, 128) == 1

@@ -1,0 +1,123 @@
+"""CPU: the oracle (oracle/gs_oracle.c) against golden vectors produced by the UNMODIFIED
+reference extension on a B200 (tests/golden/*.npz, generator: tests/golden/make_golden.py).
+This is what pins the oracle (the reference itself ships no fixtures)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def run_oracle(d, precision):
+    return oracle.forward(d["means3D"], d["opacities"], d["scales"], d["rotations"], d["view_matrix"],
+                          d["proj_matrix"], d["campos"], int(d["img_w"]), int(d["img_h"]),
+                          float(d["tanfovx"]), float(d["tanfovy"]), d["bg"],
+                          shs=d["shs"] if "shs" in d else None,
+                          colors_precomp=d["colors_precomp"] if "colors_precomp" in d else None,
+                          sh_degree=int(d["sh_degree"]), precision=precision)
+
+
+def rel(a, b):
+    den = np.linalg.norm(b)
+    return float(np.linalg.norm(np.asarray(a, np.float64) - np.asarray(b, np.float64)) / (den if den > 0 else 1.0))
+
+
+def test_golden_files_present():
+    assert len(GOLDEN) >= 5
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_oracle_matches_reference_golden(path, precision):
+    d = np.load(path)
+    r = run_oracle(d, precision)
+    vis = d["radii"] > 0
+    # integer tile / key work: bit-exact
+    assert r.num_rendered == int(d["num_rendered"])
+    assert np.array_equal(r.radii, d["radii"])
+    assert np.array_equal(r.tiles_touched.astype(np.int32), d["tiles_touched"])
+    assert np.array_equal(r.point_list.astype(np.int32), d["point_list"])
+    # keys = tile id (integer: exact) | depth bits (fp32 computed with FMA on the GPU, without
+    # on the CPU: equal to ~1 ulp)
+    gk = d["point_list_keys"].astype(np.uint64)
+    assert np.array_equal(r.keys >> np.uint64(32), gk >> np.uint64(32))
+    dep_o = (r.keys & np.uint64(0xFFFFFFFF)).astype(np.uint32).view(np.float32)
+    dep_g = (gk & np.uint64(0xFFFFFFFF)).astype(np.uint32).view(np.float32)
+    assert np.allclose(dep_o, dep_g, rtol=2e-6, atol=0)
+    assert np.array_equal(r.ranges.astype(np.int32), d["ranges"])
+    assert np.array_equal(r.n_contrib.astype(np.int32), d["n_contrib"])
+    # floating point: 1e-4 relative (observed ~1e-6)
+    assert np.abs(r.means2D[vis] - d["means2D"][vis]).max() < 1e-3
+    assert rel(r.conic_opacity[vis], d["conic_opacity"][vis]) < 1e-5
+    assert np.allclose(r.color, d["color"], rtol=1e-4, atol=2e-5)
+    assert np.allclose(r.final_T, d["final_T"], rtol=1e-4, atol=1e-5)
+    if "shs" in d:
+        assert np.abs(r.rgb[vis] - d["rgb"][vis]).max() < 1e-5
+        assert np.array_equal(r.clamped[vis].astype(np.uint8), d["clamped"][vis])
+    g = oracle.backward(r, d["grad_out"])
+    pairs = [("dL_dmean2D", d["dL_dmeans2D"][:, :2]), ("dL_dcolor", d["dL_dcolors"]),
+             ("dL_dopacity", d["dL_dopacity"]), ("dL_dmean3D", d["dL_dmeans3D"]),
+             ("dL_dcov3D", d["dL_dcov3D"]), ("dL_dsh", d["dL_dsh"]), ("dL_dscale", d["dL_dscales"]),
+             ("dL_drot", d["dL_drotations"])]
+    for name, ref in pairs:
+        if ref.size == 0:
+            continue
+        assert rel(g[name], ref) < 1e-4, name
+    assert np.all(d["dL_dmeans2D"][:, 2] == 0)
+
+
+def test_oracle_f32_f64_agree_on_larger_scene():
+    from gaussiancity_b200.synthetic import uniform_scene
+    s = uniform_scene(4000, 160, 128, sh_degree=2, seed=5)
+    a, b = oracle.forward_scene(s, "f32"), oracle.forward_scene(s, "f64")
+    assert (a.radii != b.radii).sum() <= 2
+    if a.num_rendered == b.num_rendered:
+        assert np.abs(a.color - b.color).max() < 5e-4
+
+
+def test_oracle_gradients_match_finite_differences():
+    """Independent check of the backward restatement: fp64 oracle gradient vs central finite
+    differences of the fp64 oracle forward.  The reference's semantics are discontinuous (alpha
+    < 1/255 skip, T < 1e-4 stop, 3-sigma bounding square), which makes finite differences noisy at
+    the 10 % level, so this runs the oracle's test-only smooth mode (thresholds off, wider
+    square): the differentiated formulas are the same code.  Opacity <= 0.9 keeps the 0.99 clamp
+    (through which the reference passes gradients) inactive."""
+    from gaussiancity_b200.synthetic import uniform_scene
+    s = uniform_scene(40, 48, 48, sh_degree=2, seed=9, sigma_px=(1.5, 5.0))
+    c = lambda t: t.numpy().astype(np.float64)
+    base = dict(means3D=c(s.means3D), opacities=np.minimum(c(s.opacities), 0.9), scales=c(s.scales),
+                rotations=c(s.rotations), shs=np.abs(c(s.shs)) + 0.2)   # colours never clamp
+    G = np.random.default_rng(1).standard_normal((3, 48, 48))
+
+    def loss_and_result(p):
+        r = oracle.forward(p["means3D"], p["opacities"], p["scales"], p["rotations"], c(s.view_matrix),
+                           c(s.proj_matrix), c(s.campos), 48, 48, s.tanfovx, s.tanfovy, c(s.bg),
+                           shs=p["shs"], sh_degree=2, precision="f64")
+        return float((r.color * G).sum()), r
+
+    oracle.set_smooth(True, "f64")
+    try:
+        # inputs are rounded to fp32 inside the oracle: keep every perturbed value fp32-exact
+        base = {k: v.astype(np.float32).astype(np.float64) for k, v in base.items()}
+        _, r0 = loss_and_result(base)
+        g = oracle.backward(r0, G)
+        names = {"means3D": "dL_dmean3D", "opacities": "dL_dopacity", "scales": "dL_dscale",
+                 "rotations": "dL_drot", "shs": "dL_dsh"}
+        rng = np.random.default_rng(2)
+        for key, gname in names.items():
+            direction = rng.standard_normal(base[key].shape)
+            direction /= np.linalg.norm(direction)
+            eps = 1e-3
+            plus, minus = dict(base), dict(base)
+            plus[key] = (base[key] + eps * direction).astype(np.float32).astype(np.float64)
+            minus[key] = (base[key] - eps * direction).astype(np.float32).astype(np.float64)
+            step = plus[key] - minus[key]
+            fd = loss_and_result(plus)[0] - loss_and_result(minus)[0]
+            an = float((g[gname].reshape(step.shape) * step).sum())
+            assert abs(fd - an) <= 2e-3 * max(abs(fd), abs(an)) + 1e-7, (key, fd, an)
+    finally:
+        oracle.set_smooth(False, "f64")
