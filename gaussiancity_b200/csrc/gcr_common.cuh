@@ -129,4 +129,18 @@ __forceinline__ __device__ float4 gcr_ldg_nc_f4(const float4* p) {
   return r;
 }
 
+// 256-bit global accesses (sm_100+: LDG.E.ENL2.256 / STG.E.ENL2.256): one full 32-byte sector
+// per thread per instruction; addr must be 32 B aligned.
+__forceinline__ __device__ void gcr_ldg_nc_v8(const float* p, float (&v)[8]) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]),
+                 "=f"(v[7])
+               : "l"(p));
+}
+__forceinline__ __device__ void gcr_stg_v8(float* p, const float (&v)[8]) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]),
+               "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+
 static inline size_t gcr_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

@@ -185,7 +185,18 @@ preprocess_fwd_kernel(GcrPreprocessArgs a) {
           // M=1 -> 3 floats (not a float4 multiple) so fall back to scalar loads there).
           float sh[48];
           const int nfl = a.M * 3;
-          if ((nfl & 3) == 0) {
+          if ((nfl & 7) == 0) {
+            const float* __restrict__ shp = a.shs + (size_t)idx * a.M * 3;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+              if (k * 8 < nfl) {
+                float v[8];
+                gcr_ldg_nc_v8(shp + 8 * k, v);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) sh[8 * k + i] = v[i];
+              }
+            }
+          } else if ((nfl & 3) == 0) {
 #pragma unroll
             for (int k = 0; k < 12; ++k) {
               if (k * 4 < nfl) {

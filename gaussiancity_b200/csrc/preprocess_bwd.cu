@@ -240,7 +240,26 @@ preprocess_bwd_kernel(GcrPreprocessBwdArgs a) {
       // (M = 4, 16): a quarter of the L2 transactions of the per-float access pattern.
       float ddx = 0.f, ddy = 0.f, ddz = 0.f;
       const int nfl = a.M * 3;
-      if ((nfl & 3) == 0) {
+      if ((nfl & 7) == 0) {
+        // 32-byte accesses (M = 16): every thread reads/writes whole sectors
+        const float* __restrict__ shp = a.shs + shbase;
+        float* __restrict__ dshp = a.dL_dsh + shbase;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          if (8 * q < nfl) {
+            float in[8], out[8];
+            gcr_ldg_nc_v8(shp + 8 * q, in);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int f = 8 * q + i, k = f / 3, ch = f % 3;
+              out[i] = b[k] * dRGB[ch];
+              const float t = in[i] * dRGB[ch];
+              ddx += bx[k] * t; ddy += by[k] * t; ddz += bz[k] * t;
+            }
+            gcr_stg_v8(dshp + 8 * q, out);
+          }
+        }
+      } else if ((nfl & 3) == 0) {
         const float4* __restrict__ sh4 = reinterpret_cast<const float4*>(a.shs + shbase);
         float4* __restrict__ dsh4 = reinterpret_cast<float4*>(a.dL_dsh + shbase);
 #pragma unroll
@@ -311,7 +330,10 @@ preprocess_bwd_kernel(GcrPreprocessBwdArgs a) {
     }
   } else if (kHasSH) {
     const int nfl = a.M * 3;
-    if ((nfl & 3) == 0) {
+    if ((nfl & 7) == 0) {
+      const float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int q = 0; q < nfl / 8; ++q) gcr_stg_v8(a.dL_dsh + shbase + 8 * q, z8);
+    } else if ((nfl & 3) == 0) {
       float4* __restrict__ dsh4 = reinterpret_cast<float4*>(a.dL_dsh + shbase);
       for (int q = 0; q < nfl / 4; ++q) dsh4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
     } else {

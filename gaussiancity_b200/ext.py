@@ -97,7 +97,7 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
             cov3D_precomp = _prep(cov3D_precomp, "cov3D_precomp", device)
             viewmatrix = _prep(viewmatrix, "viewmatrix", device)
             projmatrix = _prep(projmatrix, "projmatrix", device)
-            sh = _prep(sh, "sh", device, align=16)
+            sh = _prep(sh, "sh", device, align=32)
             campos = _prep(campos, "campos", device)
             rc = lib.gcr_rasterizer_forward(
                 geom.cb, None, binning.cb, None, img.cb, None,
@@ -142,7 +142,7 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
             cov3D_precomp = _prep(cov3D_precomp, "cov3D_precomp", device)
             viewmatrix = _prep(viewmatrix, "viewmatrix", device)
             projmatrix = _prep(projmatrix, "projmatrix", device)
-            sh = _prep(sh, "sh", device, align=16)
+            sh = _prep(sh, "sh", device, align=32)
             campos = _prep(campos, "campos", device)
             dL_dout_color = _prep(dL_dout_color, "dL_dout_color", device)
             radii = radii.contiguous()
@@ -233,7 +233,7 @@ def rasterize_gaussians_backward_geometry(means3D, radii, scales, rotations, sca
             cov3D_precomp = _prep(cov3D_precomp, "cov3D_precomp", device)
             viewmatrix = _prep(viewmatrix, "viewmatrix", device)
             projmatrix = _prep(projmatrix, "projmatrix", device)
-            sh = _prep(sh, "sh", device, align=16)
+            sh = _prep(sh, "sh", device, align=32)
             campos = _prep(campos, "campos", device)
             rc = lib.gcr_rasterizer_backward_geometry(
                 P, int(degree), M, _ptr(means3D), _ptr(sh), _ptr(scales), float(scale_modifier),

@@ -162,6 +162,38 @@ class TileShardedRasterizer:
         self._note_R(state)
         return color, grads, sl
 
+    # -- frame pipelining: the broadcast of frame i+1 overlaps the compute of frame i --------
+    def start_prefetch(self, inp_next, src=0):
+        """Issue the per-frame broadcast of `inp_next` on a side stream (NCCL's own stream is
+        ordered after it, not after the compute stream). Returns a handle for wait_prefetch().
+        `inp_next` must not be read or written by the compute stream until then."""
+        if self.world == 1:
+            return None
+        if not hasattr(self, "_comm_stream"):
+            self._comm_stream = torch.cuda.Stream(device=self.device)
+        cur = torch.cuda.current_stream(self.device)
+        self._comm_stream.wait_stream(cur)   # the buffers' previous readers (frame i-1) are done
+        works = []
+        with torch.cuda.stream(self._comm_stream):
+            for k in sorted(inp_next):
+                t = inp_next[k]
+                if isinstance(t, torch.Tensor) and t.numel() > 0:
+                    works.append(dist.broadcast(t, src=src, group=self.group, async_op=True))
+        return works
+
+    def wait_prefetch(self, handle):
+        if handle:
+            for w in handle:
+                w.wait()   # makes the current (compute) stream wait for the broadcast
+
+    def forward_backward_prefetched(self, s, inp, grad_out):
+        """forward_backward on buffers whose broadcast was started with start_prefetch()."""
+        cam = self._cam(s, inp)
+        color, radii, state = self.render(inp, cam, broadcast=False)
+        grads, sl = self.backward(state, inp, cam, grad_out)
+        self._note_R(state)
+        return color, grads, sl
+
     def _note_R(self, state):
         self.last_num_rendered_local = int(state["R"])
         self.last_num_rendered_total = self.last_num_rendered_local
