@@ -42,6 +42,9 @@ WORKLOADS = {
     "cfg2_100k_sh0_512": (100_000, 512, 512, 0, True),
     "city_5M_precomp_1080p": (5_000_000, 1920, 1080, 0, False),
     "tiny": (20_000, 256, 256, 1, True),
+    # GaussianCity's own call pattern (BASELINE config 5 scale): lattice points, K/sensor camera
+    "cfg5_city_16k_540p": (16_384, 960, 540, 0, False),
+    "city_500k_540p": (500_000, 960, 540, 0, False),
 }
 DEFAULT_WORKLOAD = "cfg4_5M_sh3_1080p"
 
@@ -121,8 +124,10 @@ def kernels_per_step(W, H, backward=True):
 
 # ------------------------------------------------------------------------------------------
 def make_scene(name, device):
-    from gaussiancity_b200.synthetic import uniform_scene
+    from gaussiancity_b200.synthetic import city_scene, uniform_scene
     P, W, H, deg, use_sh = WORKLOADS[name]
+    if "city" in name and "precomp" not in name:
+        return city_scene(P, seed=0, device=device)
     return uniform_scene(P, W, H, sh_degree=deg, seed=0, device=device, use_sh=use_sh)
 
 
@@ -417,8 +422,15 @@ def main():
             dom = max(("blend_bwd", "blend_fwd"), key=lambda k: stages.get(k, 0.0))
             dur = stages[dom]
             achieved = alg[dom] / (dur * 1e-3) / 1e9
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+            if os.path.exists(tpath):
+                with open(tpath) as fh:
+                    tj = json.load(fh)
+                if tj.get("workload") == args.workload:   # per-launch DRAM bytes from the committed
+                    traffic = tj["kernels"].get(dom, {}).get("dram_bytes")   # ncu --set full capture
             line["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak,
-                                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                                 "peak_source": peak_src, "kernel_ms": dur,
                                 "algorithmic_bytes": alg[dom],
                                 "note": "blend kernels are fp32-issue/L2-reduction bound (~160 FLOP "

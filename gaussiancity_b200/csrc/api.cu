@@ -271,10 +271,12 @@ int gcr_rasterizer_forward(gcr_alloc_fn geometryBuffer, void* geometry_ctx,
 
   // 4. R to the host (sizes the binning buffer; same sync as rasterizer_impl.cu:235-238)
   ht.lap("launch_pre");
-  uint32_t num_rendered_u = 0;
-  GCR_CUDA_OK(cudaMemcpyAsync(&num_rendered_u, offsets + (P - 1), sizeof(uint32_t),
-                              cudaMemcpyDeviceToHost, stream));
+  static thread_local uint32_t* pinned_R = nullptr;   // pinned: the D2H copy is a true async DMA
+  if (pinned_R == nullptr) GCR_CUDA_OK(cudaHostAlloc(&pinned_R, sizeof(uint32_t), cudaHostAllocDefault));
+  GCR_CUDA_OK(cudaMemcpyAsync(pinned_R, offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                              stream));
   GCR_CUDA_OK(cudaStreamSynchronize(stream));
+  const uint32_t num_rendered_u = *pinned_R;
   ht.lap("sync_R");
   if (num_rendered_u > 0x7fffffffu) return fail("num_rendered exceeds int32");
   const size_t R = num_rendered_u;

@@ -11,6 +11,8 @@
 // R 8-byte pairs at 1080p) finishes the job.  A stable sort on (tile, depth) of index-ordered
 // input equals a stable depth sort followed by a stable tile sort, so point_list and ranges are
 // bit-identical to the reference's, ties included, at ~1/3 of the HBM traffic.
+#include <cstdlib>
+
 #include "gcr_common.cuh"
 #include "gcr_kernels.h"
 
@@ -47,6 +49,22 @@ __device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* sm
   *total = smem[8];
   __syncthreads();
   return res;
+}
+
+// Lanes of `vmask` holding the same `nbits`-bit digit as the caller.  Built from one ballot per
+// digit bit: on sm_100 MATCH.ANY resolves one distinct value at a time (hundreds of cycles for a
+// high-entropy digit, measured: it bounded the whole sort), ballots pipeline.
+__device__ __forceinline__ unsigned digit_peers(uint32_t d, int nbits, unsigned vmask) {
+  unsigned peers = vmask;
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    if (b < nbits) {
+      const bool bit = (d >> b) & 1u;
+      const unsigned bal = __ballot_sync(vmask, bit);
+      peers &= bit ? bal : ~bal;
+    }
+  }
+  return peers;
 }
 
 __device__ __forceinline__ uint32_t scan_load(const uint32_t* __restrict__ in,
@@ -117,20 +135,27 @@ constexpr int kBins = 256;
 
 __global__ void __launch_bounds__(kSortThreads)
 radix_hist_kernel(const uint32_t* __restrict__ keys, size_t n, int shift, uint32_t digit_mask,
-                  uint32_t* __restrict__ table, uint32_t nblk) {
+                  int nbits, uint32_t* __restrict__ table, uint32_t nblk) {
   __shared__ uint32_t hist[kBins];
   hist[threadIdx.x] = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const size_t base = (size_t)blockIdx.x * kSortChunk + (size_t)warp * (32 * kSortItems);
-#pragma unroll 4
+  // issue all loads first: ballots are convergence points the compiler does not hoist loads over
+  uint32_t key[kSortItems];
+#pragma unroll
+  for (int r = 0; r < kSortItems; ++r) {
+    const size_t i = base + (size_t)r * 32 + lane;
+    key[r] = i < n ? keys[i] : 0u;
+  }
+#pragma unroll
   for (int r = 0; r < kSortItems; ++r) {
     const size_t i = base + (size_t)r * 32 + lane;
     const bool valid = i < n;
     const unsigned vmask = __ballot_sync(0xffffffffu, valid);
     if (valid) {
-      const uint32_t d = (keys[i] >> shift) & digit_mask;
-      const unsigned m = __match_any_sync(vmask, d);
+      const uint32_t d = (key[r] >> shift) & digit_mask;
+      const unsigned m = digit_peers(d, nbits, vmask);
       if ((m & ((1u << lane) - 1)) == 0) atomicAdd(&hist[d], (uint32_t)__popc(m));
     }
   }
@@ -159,7 +184,7 @@ template <bool kIota>
 __global__ void __launch_bounds__(kSortThreads)
 radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                      uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, size_t n,
-                     int shift, uint32_t digit_mask, const uint32_t* __restrict__ table,
+                     int shift, uint32_t digit_mask, int nbits, const uint32_t* __restrict__ table,
                      uint32_t nblk, const uint32_t* __restrict__ totals) {
   __shared__ uint32_t warp_hist[8][kBins];   // per-warp digit counts -> per-warp prefixes
   __shared__ uint32_t gbase[kBins];          // global output base of this block's digit run
@@ -178,18 +203,20 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
   uint32_t key[kSortItems], val[kSortItems];
   uint16_t rank[kSortItems];
 #pragma unroll
+  for (int r = 0; r < kSortItems; ++r) {   // all loads in flight before the first ballot
+    const size_t i = base + (size_t)r * 32 + lane;
+    key[r] = i < n ? keys_in[i] : 0u;
+    val[r] = kIota ? (uint32_t)i : (i < n ? vals_in[i] : 0u);
+  }
+#pragma unroll
   for (int r = 0; r < kSortItems; ++r) {
     const size_t i = base + (size_t)r * 32 + lane;
     const bool valid = i < n;
     const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-    key[r] = 0;
-    val[r] = 0;
     rank[r] = 0;
     if (valid) {
-      key[r] = keys_in[i];
-      val[r] = kIota ? (uint32_t)i : vals_in[i];
       const uint32_t d = (key[r] >> shift) & digit_mask;
-      const unsigned m = __match_any_sync(vmask, d);
+      const unsigned m = digit_peers(d, nbits, vmask);
       const uint32_t before = warp_hist[warp][d];
       rank[r] = (uint16_t)(before + __popc(m & ((1u << lane) - 1)));
       __syncwarp(vmask);
@@ -235,6 +262,364 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
     const size_t dst = (size_t)gbase[d] + (i - bstart[d]);
     keys_out[dst] = k;
     vals_out[dst] = st_vals[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Onesweep-style passes (Adinets & Merrill): ONE histogram kernel computes the global digit
+// histograms of every pass (they are permutation invariant), then each pass is a single kernel
+// whose blocks obtain their output offsets with a chained scan / decoupled look-back over a
+// per-tile status word instead of a separate histogram + scan launch.  16 B/pair/pass of HBM
+// traffic and 1 + passes launches per sort (was 20 B and 3 x passes).  Tiles are handed out by
+// an atomic ticket so a tile's predecessors have always started: the look-back cannot deadlock.
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t kFlagAgg = 1u << 30, kFlagIncl = 2u << 30, kValMask = (1u << 30) - 1u;
+constexpr int kMaxPasses = 4;
+
+__global__ void __launch_bounds__(kSortThreads)
+radix_hist_all_kernel(const uint32_t* __restrict__ keys, size_t n, int end_bit,
+                      uint32_t* __restrict__ ghist /* [kMaxPasses][kBins] */) {
+  __shared__ uint32_t hist[kMaxPasses][kBins];
+#pragma unroll
+  for (int p = 0; p < kMaxPasses; ++p) hist[p][threadIdx.x] = 0;
+  __syncthreads();
+  const int npass = (end_bit + 7) / 8;
+  const size_t nchunks = (n + kSortChunk - 1) / kSortChunk;
+  for (size_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    const size_t base = c * kSortChunk + threadIdx.x;
+    uint32_t key[kSortItems];
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+      const size_t i = base + (size_t)r * kSortThreads;
+      key[r] = i < n ? keys[i] : 0u;
+    }
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+      const size_t i = base + (size_t)r * kSortThreads;
+      if (i < n) {
+#pragma unroll
+        for (int p = 0; p < kMaxPasses; ++p) {
+          if (p < npass) {
+            const int bits = min(8, end_bit - 8 * p);
+            atomicAdd(&hist[p][(key[r] >> (8 * p)) & ((1u << bits) - 1u)], 1u);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int p = 0; p < kMaxPasses; ++p)
+    if (p < npass && hist[p][threadIdx.x] != 0) atomicAdd(&ghist[p * kBins + threadIdx.x], hist[p][threadIdx.x]);
+}
+
+template <bool kIota>
+__global__ void __launch_bounds__(kSortThreads, 4)
+onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, size_t n,
+                     int shift, uint32_t digit_mask, int nbits,
+                     const uint32_t* __restrict__ ghist_pass /* [kBins] */,
+                     volatile uint32_t* status /* [tiles][kBins], zeroed */, uint32_t* ticket) {
+  __shared__ uint32_t warp_hist[8][kBins];
+  __shared__ uint32_t gbase[kBins];
+  __shared__ uint32_t bstart[kBins];
+  __shared__ uint32_t sm[16];
+  __shared__ uint32_t st_keys[kSortChunk];
+  __shared__ uint32_t st_vals[kSortChunk];
+  __shared__ uint32_t s_tile;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+#pragma unroll
+  for (int w = 0; w < 8; ++w) warp_hist[w][tid] = 0;
+  __syncthreads();
+  const uint32_t tile = s_tile;
+
+  const size_t chunk_base = (size_t)tile * kSortChunk;
+  const size_t base = chunk_base + (size_t)warp * (32 * kSortItems);
+  // keys stay in registers across the ranking; values are fetched only when they are staged
+  // (keeps the kernel at <= 64 registers -> 4 CTAs/SM; it is bandwidth/latency bound)
+  uint32_t key[kSortItems];
+  uint16_t rank[kSortItems];
+#pragma unroll
+  for (int r = 0; r < kSortItems; ++r) {
+    const size_t i = base + (size_t)r * 32 + lane;
+    key[r] = i < n ? keys_in[i] : 0u;
+  }
+#pragma unroll
+  for (int r = 0; r < kSortItems; ++r) {
+    const size_t i = base + (size_t)r * 32 + lane;
+    const bool valid = i < n;
+    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+    rank[r] = 0;
+    if (valid) {
+      const uint32_t d = (key[r] >> shift) & digit_mask;
+      const unsigned m = digit_peers(d, nbits, vmask);
+      const uint32_t before = warp_hist[warp][d];
+      rank[r] = (uint16_t)(before + __popc(m & ((1u << lane) - 1)));
+      __syncwarp(vmask);
+      if ((m & ((1u << lane) - 1)) == 0) warp_hist[warp][d] = before + __popc(m);
+      __syncwarp(vmask);
+    }
+  }
+  __syncthreads();
+
+  {
+    uint32_t acc = 0;   // this tile's count of digit `tid`
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const uint32_t t = warp_hist[w][tid];
+      warp_hist[w][tid] = acc;
+      acc += t;
+    }
+    uint32_t dummy;
+    bstart[tid] = block_excl_scan_256(acc, sm, &dummy);
+    const uint32_t dstart = block_excl_scan_256(ghist_pass[tid], sm, &dummy);
+    // decoupled look-back over the predecessors' status words for this digit
+    volatile uint32_t* mine = status + (size_t)tile * kBins + tid;
+    uint32_t excl = 0;
+    if (tile == 0) {
+      *mine = kFlagIncl | acc;
+    } else {
+      *mine = kFlagAgg | acc;
+      long long t = (long long)tile - 1;
+      while (true) {
+        const uint32_t v = status[(size_t)t * kBins + tid];
+        const uint32_t f = v & ~kValMask;
+        if (f == 0u) continue;              // predecessor has not published yet: spin
+        excl += v & kValMask;
+        if (f == kFlagIncl) break;
+        --t;
+      }
+      *mine = kFlagIncl | (excl + acc);
+    }
+    gbase[tid] = dstart + excl;
+  }
+  __syncthreads();
+
+  {
+    uint32_t val[kSortItems];
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+      const size_t i = base + (size_t)r * 32 + lane;
+      val[r] = kIota ? (uint32_t)i : (i < n ? vals_in[i] : 0u);
+    }
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+      const size_t i = base + (size_t)r * 32 + lane;
+      if (i < n) {
+        const uint32_t d = (key[r] >> shift) & digit_mask;
+        const uint32_t pos = bstart[d] + warp_hist[warp][d] + rank[r];
+        st_keys[pos] = key[r];
+        st_vals[pos] = val[r];
+      }
+    }
+  }
+  __syncthreads();
+
+  const uint32_t count = (uint32_t)min((size_t)kSortChunk, n - chunk_base);
+  for (uint32_t i = tid; i < count; i += kSortThreads) {
+    const uint32_t k = st_keys[i];
+    const uint32_t d = (k >> shift) & digit_mask;
+    const size_t dst = (size_t)gbase[d] + (i - bstart[d]);
+    keys_out[dst] = k;
+    vals_out[dst] = st_vals[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Small inputs (GaussianCity's own regime: P <= 16 384 points per frame, R of a few 10^4):
+// the multi-kernel sort above is launch-latency bound (3 launches per digit pass), so all digit
+// passes run inside ONE single-CTA kernel: 32 warps, chunks of 16 384 items, the same stable
+// match-any ranking, ping-pong through global memory (L2 resident at this size).
+// ------------------------------------------------------------------------------------------
+constexpr int kSmallThreads = 1024;
+constexpr int kSmallWarps = kSmallThreads / 32;
+constexpr int kSmallRounds = 16;
+constexpr int kSmallChunk = kSmallThreads * kSmallRounds;  // 16384
+constexpr int kSmallMaxChunks = 4;
+constexpr size_t kSmallSortMaxN = (size_t)kSmallChunk * kSmallMaxChunks;  // 65536
+// Measured on B200 (profiles/r01_small_scenes.md): a single SM is slower than the multi-block
+// path even at 16 k items (one CTA cannot hide its own L2 round trips), so the single-CTA kernels
+// are kept for reference but disabled; env GCR_SMALL_SORT=1 re-enables them for experiments.
+static bool small_paths_enabled() {
+  static const bool on = getenv("GCR_SMALL_SORT") != nullptr;
+  return on;
+}
+constexpr int kSmallSortSmem = (kSmallWarps * kBins + kSmallMaxChunks * kBins + kBins) * 4 + kSmallChunk * 2;
+
+template <bool kIotaFirst>
+__global__ void __launch_bounds__(kSmallThreads)
+small_sort_kernel(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, uint32_t n,
+                  int end_bit) {
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  uint32_t (*warp_hist)[kBins] = reinterpret_cast<uint32_t (*)[kBins]>(sm_raw);
+  uint32_t (*chunk_base)[kBins] = reinterpret_cast<uint32_t (*)[kBins]>(sm_raw + kSmallWarps * kBins * 4);
+  uint32_t* digit_tot = reinterpret_cast<uint32_t*>(sm_raw + (kSmallWarps + kSmallMaxChunks) * kBins * 4);
+  uint16_t* ranks = reinterpret_cast<uint16_t*>(sm_raw + (kSmallWarps + kSmallMaxChunks + 1) * kBins * 4);
+  __shared__ uint32_t scan_tmp[40];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t nchunks = (n + kSmallChunk - 1) / kSmallChunk;
+  uint32_t* kin = keys_a; uint32_t* vin = vals_a; uint32_t* kout = keys_b; uint32_t* vout = vals_b;
+
+  for (int shift = 0; shift < end_bit; shift += 8) {
+    const int nbits = min(8, end_bit - shift);
+    const uint32_t dmask = (1u << nbits) - 1u;
+    // ---- sweep 1: per-chunk digit counts (skipped for a single chunk) ----
+    if (nchunks > 1) {
+      for (int i = tid; i < kSmallMaxChunks * kBins; i += kSmallThreads) (&chunk_base[0][0])[i] = 0;
+      __syncthreads();
+      for (uint32_t c = 0; c < nchunks; ++c) {
+        uint32_t k1[kSmallRounds];
+#pragma unroll
+        for (int r = 0; r < kSmallRounds; ++r) {
+          const uint32_t i = c * kSmallChunk + warp * (32 * kSmallRounds) + r * 32 + lane;
+          k1[r] = i < n ? kin[i] : 0u;
+        }
+#pragma unroll
+        for (int r = 0; r < kSmallRounds; ++r) {
+          const uint32_t i = c * kSmallChunk + warp * (32 * kSmallRounds) + r * 32 + lane;
+          const bool valid = i < n;
+          const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+          if (valid) {
+            const uint32_t d = (k1[r] >> shift) & dmask;
+            const unsigned m = digit_peers(d, nbits, vmask);
+            if ((m & ((1u << lane) - 1)) == 0) atomicAdd(&chunk_base[c][d], (uint32_t)__popc(m));
+          }
+        }
+      }
+      __syncthreads();
+    }
+    // ---- sweep 2: rank + scatter, chunk by chunk ----
+    for (uint32_t c = 0; c < nchunks; ++c) {
+      for (int i = tid; i < kSmallWarps * kBins; i += kSmallThreads) (&warp_hist[0][0])[i] = 0;
+      // all loads of the chunk are issued up front (16 independent requests per thread): a
+      // single CTA has no other warps to hide L2 latency behind
+      uint32_t key[kSmallRounds], val[kSmallRounds];
+      const uint32_t loc0 = warp * (32 * kSmallRounds) + lane;
+#pragma unroll
+      for (int r = 0; r < kSmallRounds; ++r) {
+        const uint32_t i = c * kSmallChunk + loc0 + r * 32;
+        key[r] = i < n ? kin[i] : 0u;
+        val[r] = (kIotaFirst && shift == 0) ? i : (i < n ? vin[i] : 0u);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < kSmallRounds; ++r) {
+        const uint32_t loc = loc0 + r * 32;
+        const bool valid = c * kSmallChunk + loc < n;
+        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+          const uint32_t d = (key[r] >> shift) & dmask;
+          const unsigned m = digit_peers(d, nbits, vmask);
+          const uint32_t before = warp_hist[warp][d];
+          ranks[loc] = (uint16_t)(before + __popc(m & ((1u << lane) - 1)));
+          __syncwarp(vmask);
+          if ((m & ((1u << lane) - 1)) == 0) warp_hist[warp][d] = before + __popc(m);
+          __syncwarp(vmask);
+        }
+      }
+      __syncthreads();
+      // digit tid: exclusive prefix over warps; chunk total
+      uint32_t tot = 0;
+      if (tid < kBins) {
+#pragma unroll 4
+        for (int w = 0; w < kSmallWarps; ++w) {
+          const uint32_t t = warp_hist[w][tid];
+          warp_hist[w][tid] = tot;
+          tot += t;
+        }
+      }
+      __syncthreads();
+      if (nchunks == 1 || c == 0) {
+        // global digit starts: exclusive scan over digits of the per-digit totals of ALL chunks
+        uint32_t all = tot;
+        if (nchunks > 1 && tid < kBins) {
+          all = 0;
+          for (uint32_t cc = 0; cc < nchunks; ++cc) all += chunk_base[cc][tid];
+        }
+        uint32_t v = (tid < kBins) ? all : 0;
+        uint32_t inc = warp_incl_scan(v, lane);
+        if (tid < kBins && lane == 31) scan_tmp[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+          uint32_t wv = (lane < 8) ? scan_tmp[lane] : 0;
+          uint32_t winc = warp_incl_scan(wv, lane);
+          if (lane < 8) scan_tmp[lane] = winc - wv;
+        }
+        __syncthreads();
+        if (tid < kBins) digit_tot[tid] = inc - v + scan_tmp[warp];   // digit start
+        __syncthreads();
+        if (nchunks > 1 && tid < kBins) {
+          uint32_t run = digit_tot[tid];
+          for (uint32_t cc = 0; cc < nchunks; ++cc) {
+            const uint32_t t = chunk_base[cc][tid];
+            chunk_base[cc][tid] = run;
+            run += t;
+          }
+        }
+        __syncthreads();
+      }
+#pragma unroll
+      for (int r = 0; r < kSmallRounds; ++r) {
+        const uint32_t loc = loc0 + r * 32;
+        if (c * kSmallChunk + loc < n) {
+          const uint32_t d = (key[r] >> shift) & dmask;
+          const uint32_t base = (nchunks > 1) ? chunk_base[c][d] : digit_tot[d];
+          const uint32_t dst = base + warp_hist[warp][d] + ranks[loc];
+          kout[dst] = key[r];
+          vout[dst] = val[r];
+        }
+      }
+      __syncthreads();
+    }
+    __threadfence_block();
+    __syncthreads();
+    uint32_t* t = kin; kin = kout; kout = t;
+    t = vin; vin = vout; vout = t;
+  }
+}
+
+// single-CTA inclusive scan (with optional gather) for n <= 65536: 16 consecutive items per
+// thread, all (gathered) loads issued before the first dependent instruction
+__global__ void __launch_bounds__(kSmallThreads)
+small_scan_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ gather, uint32_t n,
+                  uint32_t* __restrict__ out) {
+  __shared__ uint32_t wsum[kSmallWarps];
+  __shared__ uint32_t carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < n; base += kSmallChunk) {
+    const uint32_t i0 = base + tid * kSmallRounds;
+    uint32_t v[kSmallRounds];
+#pragma unroll
+    for (int k = 0; k < kSmallRounds; ++k) {
+      const uint32_t i = i0 + k;
+      v[k] = i < n ? (gather ? in[gather[i]] : in[i]) : 0u;
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < kSmallRounds; ++k) s += v[k];
+    const uint32_t inc = warp_incl_scan(s, lane);
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      const uint32_t w = wsum[lane];
+      const uint32_t winc = warp_incl_scan(w, lane);
+      wsum[lane] = winc - w;
+    }
+    __syncthreads();
+    uint32_t run = inc - s + wsum[warp] + carry_s;
+#pragma unroll
+    for (int k = 0; k < kSmallRounds; ++k) {
+      run += v[k];
+      if (i0 + k < n) out[i0 + k] = run;
+    }
+    __syncthreads();
+    if (tid == kSmallThreads - 1) carry_s = run;
+    __syncthreads();
   }
 }
 
@@ -300,6 +685,10 @@ size_t gcr_scan_workspace_bytes(size_t n) {
 void gcr_launch_inclusive_scan(const uint32_t* in, const uint32_t* gather, uint32_t* out, size_t n,
                                void* workspace, cudaStream_t stream) {
   if (n == 0) return;
+  if (n <= kSmallSortMaxN && small_paths_enabled()) {
+    small_scan_kernel<<<1, kSmallThreads, 0, stream>>>(in, gather, (uint32_t)n, out);
+    return;
+  }
   const size_t nb = (n + kScanChunk - 1) / kScanChunk;
   uint32_t* sums = static_cast<uint32_t*>(workspace);
   scan_reduce_kernel<<<(unsigned)nb, kScanThreads, 0, stream>>>(in, gather, n, sums);
@@ -309,14 +698,54 @@ void gcr_launch_inclusive_scan(const uint32_t* in, const uint32_t* gather, uint3
 
 size_t gcr_sort_workspace_bytes(size_t n) {
   const size_t nblk = (n + kSortChunk - 1) / kSortChunk;
-  return gcr_align_up((nblk * kBins + kBins) * sizeof(uint32_t), 256);
+  // onesweep: global histograms [4][256] + tickets [4] (+pad) + status [4][nblk][256]
+  return gcr_align_up((kMaxPasses * kBins + 64 + kMaxPasses * nblk * kBins) * sizeof(uint32_t), 256);
 }
 
 int gcr_launch_radix_sort(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b,
                           size_t n, int end_bit, bool vals_iota, void* workspace,
                           cudaStream_t stream) {
   if (n == 0) return 0;
+  if (end_bit <= 0) end_bit = 1;  // at least one pass so values are materialised
+  if (n <= kSmallSortMaxN && small_paths_enabled()) {
+    static const bool configured = [] {
+      cudaFuncSetAttribute(small_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallSortSmem);
+      cudaFuncSetAttribute(small_sort_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallSortSmem);
+      return true;
+    }();
+    (void)configured;
+    if (vals_iota)
+      small_sort_kernel<true><<<1, kSmallThreads, kSmallSortSmem, stream>>>(keys_a, vals_a, keys_b, vals_b, (uint32_t)n, end_bit);
+    else
+      small_sort_kernel<false><<<1, kSmallThreads, kSmallSortSmem, stream>>>(keys_a, vals_a, keys_b, vals_b, (uint32_t)n, end_bit);
+    return ((end_bit + 7) / 8) & 1;
+  }
   const uint32_t nblk = (uint32_t)((n + kSortChunk - 1) / kSortChunk);
+  static const bool classic = getenv("GCR_SORT_CLASSIC") != nullptr;
+  if (!classic && n < (size_t)kValMask && end_bit <= 8 * kMaxPasses) {
+    uint32_t* ws = static_cast<uint32_t*>(workspace);
+    uint32_t* ghist = ws;
+    uint32_t* tickets = ws + kMaxPasses * kBins;
+    uint32_t* status = ws + kMaxPasses * kBins + 64;
+    const int npass = (end_bit + 7) / 8;
+    cudaMemsetAsync(ws, 0, (kMaxPasses * kBins + 64 + (size_t)npass * nblk * kBins) * sizeof(uint32_t), stream);
+    const unsigned hgrid = (unsigned)min((size_t)nblk, (size_t)148 * 8);
+    radix_hist_all_kernel<<<hgrid, kSortThreads, 0, stream>>>(keys_a, n, end_bit, ghist);
+    uint32_t* kin = keys_a; uint32_t* vin = vals_a; uint32_t* kout = keys_b; uint32_t* vout = vals_b;
+    for (int p = 0; p < npass; ++p) {
+      const int shift = 8 * p;
+      const int bits = min(8, end_bit - shift);
+      const uint32_t mask = (1u << bits) - 1u;
+      uint32_t* st = status + (size_t)p * nblk * kBins;
+      if (vals_iota && p == 0)
+        onesweep_pass_kernel<true><<<nblk, kSortThreads, 0, stream>>>(kin, vin, kout, vout, n, shift, mask, bits, ghist + p * kBins, st, tickets + p);
+      else
+        onesweep_pass_kernel<false><<<nblk, kSortThreads, 0, stream>>>(kin, vin, kout, vout, n, shift, mask, bits, ghist + p * kBins, st, tickets + p);
+      uint32_t* t = kin; kin = kout; kout = t;
+      t = vin; vin = vout; vout = t;
+    }
+    return npass & 1;
+  }
   uint32_t* table = static_cast<uint32_t*>(workspace);
   uint32_t* totals = table + (size_t)nblk * kBins;
   uint32_t* kin = keys_a;
@@ -324,18 +753,17 @@ int gcr_launch_radix_sort(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, 
   uint32_t* kout = keys_b;
   uint32_t* vout = vals_b;
   int where = 0;
-  if (end_bit <= 0) end_bit = 1;  // at least one pass so values are materialised
   for (int shift = 0; shift < end_bit; shift += 8) {
     const int bits = min(8, end_bit - shift);
     const uint32_t mask = (1u << bits) - 1u;
-    radix_hist_kernel<<<nblk, kSortThreads, 0, stream>>>(kin, n, shift, mask, table, nblk);
+    radix_hist_kernel<<<nblk, kSortThreads, 0, stream>>>(kin, n, shift, mask, bits, table, nblk);
     radix_scan_rows_kernel<<<kBins, kSortThreads, 0, stream>>>(table, nblk, totals);
     if (vals_iota && shift == 0)
       radix_scatter_kernel<true><<<nblk, kSortThreads, 0, stream>>>(kin, vin, kout, vout, n, shift,
-                                                                    mask, table, nblk, totals);
+                                                                    mask, bits, table, nblk, totals);
     else
       radix_scatter_kernel<false><<<nblk, kSortThreads, 0, stream>>>(kin, vin, kout, vout, n, shift,
-                                                                     mask, table, nblk, totals);
+                                                                     mask, bits, table, nblk, totals);
     uint32_t* t = kin; kin = kout; kout = t;
     t = vin; vin = vout; vout = t;
     where ^= 1;

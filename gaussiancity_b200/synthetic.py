@@ -149,3 +149,20 @@ def _matrix_to_quat_xyzw(R):
         x, y, z = q
     q = np.array([x, y, z, w])
     return q / np.linalg.norm(q)
+
+
+def city_scene(P, seed=0, device="cpu", scale=1.0, extent=256):
+    """The GaussianCity call pattern as a Scene: lattice points through the K / sensor camera
+    adapter (negative clip-space w), colours precomputed in (-1,1), identity quaternions,
+    opacity 1 (reference utils/helpers.py:226-247 + DGR/__init__.py:382-426)."""
+    from . import GaussianRasterizerWrapper
+    K = CITY_K.copy()
+    K[:2] *= scale
+    sensor = (int(CITY_SENSOR[0] * scale), int(CITY_SENSOR[1] * scale))
+    pts, cam_pos, cam_quat = city_points(P, seed=seed, extent=extent, device=device)
+    wrap = GaussianRasterizerWrapper(K, sensor, device=torch.device(device) if isinstance(device, str) else device)
+    st = wrap._get_gaussian_rasterization_settings(cam_pos, cam_quat)
+    return Scene(pts[:, 0:3].contiguous(), pts[:, 4:7].contiguous(), pts[:, 7:11].contiguous(),
+                 pts[:, 3:4].contiguous(), None, pts[:, 11:14].contiguous(), 0, st.img_w, st.img_h,
+                 st.tanfovx, st.tanfovy, st.view_matrix.contiguous(), st.proj_matrix.contiguous(),
+                 st.campos.contiguous(), st.bg)
