@@ -624,6 +624,11 @@ small_scan_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------
+// One warp expands 32 consecutive depth-ordered Gaussians: their instances occupy ONE contiguous
+// output span (offsets are a scan in this order), so lanes stride over the span's elements, find
+// the owning Gaussian by a shuffle binary search over the lanes' start offsets, and write fully
+// coalesced (the per-thread loop of the reference, rasterizer_impl.cu:85-98, writes 32 scattered
+// runs per instruction).  Row-major over the tile rect, owned tile rows only.
 __global__ void __launch_bounds__(256)
 emit_pairs_kernel(int P, const uint32_t* __restrict__ sorted_gauss,
                   const uint32_t* __restrict__ offsets_incl,
@@ -631,21 +636,55 @@ emit_pairs_kernel(int P, const uint32_t* __restrict__ sorted_gauss,
                   const GcrRecord* __restrict__ records, const int* __restrict__ radii, int grid_x,
                   int grid_y, int shard_rank, int shard_count, uint32_t* __restrict__ tile_keys,
                   uint32_t* __restrict__ gauss_vals) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P) return;
-  const uint32_t g = sorted_gauss[i];
-  const uint32_t n = tiles_touched[g];
-  if (n == 0) return;
-  uint32_t off = offsets_incl[i] - n;
-  const float4 q0 = records[g].q0;
-  uint2 rmin, rmax;
-  gcr_get_rect(q0.x, q0.y, radii[g], grid_x, grid_y, rmin, rmax);
-  for (uint32_t y = rmin.y; y < rmax.y; ++y) {
-    if (shard_count > 1 && (int)(y % (uint32_t)shard_count) != shard_rank) continue;
-    for (uint32_t x = rmin.x; x < rmax.x; ++x) {
-      tile_keys[off] = y * grid_x + x;
-      gauss_vals[off] = g;
-      ++off;
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;      // warp covers i0 .. i0+31
+  uint32_t g = 0, n = 0, end = 0, x0 = 0, w = 1, y0 = 0;
+  if (i < P) {
+    g = sorted_gauss[i];
+    n = tiles_touched[g];
+    end = offsets_incl[i];
+    if (n != 0) {
+      const float4 q0 = records[g].q0;
+      uint2 rmin, rmax;
+      gcr_get_rect(q0.x, q0.y, radii[g], grid_x, grid_y, rmin, rmax);
+      x0 = rmin.x;
+      w = rmax.x - rmin.x;
+      // first owned tile row >= rmin.y (all rows are owned when shard_count == 1)
+      y0 = rmin.y;
+      if (shard_count > 1) {
+        const uint32_t m = rmin.y % (uint32_t)shard_count;
+        y0 = rmin.y + (((uint32_t)shard_rank + (uint32_t)shard_count - m) % (uint32_t)shard_count);
+      }
+    }
+  }
+  // inclusive end offsets are non-decreasing across lanes; lanes past P repeat the last end
+  const uint32_t last_end = __shfl_sync(0xffffffffu, end, min(31, max(0, P - 1 - (i - lane))));
+  if (i >= P) end = last_end;
+  const uint32_t start = end - n;
+  const uint32_t span0 = __shfl_sync(0xffffffffu, start, 0);
+  const uint32_t span1 = __shfl_sync(0xffffffffu, end, 31);
+  for (uint32_t eb = span0; eb < span1; eb += 32) {   // warp-uniform trip count (full-mask shuffles)
+    const bool act = eb + lane < span1;
+    const uint32_t e = act ? eb + lane : span1 - 1;
+    // owner = first lane whose inclusive end exceeds e  (lanes with n == 0 have end == start)
+    int lo = 0, hi = 31;
+#pragma unroll
+    for (int it = 0; it < 5; ++it) {
+      const int mid = (lo + hi) >> 1;
+      const uint32_t em = __shfl_sync(0xffffffffu, end, mid);
+      if (em > e) hi = mid; else lo = mid + 1;
+    }
+    const int own = lo;
+    const uint32_t os = __shfl_sync(0xffffffffu, start, own);
+    const uint32_t og = __shfl_sync(0xffffffffu, g, own);
+    const uint32_t ox0 = __shfl_sync(0xffffffffu, x0, own);
+    const uint32_t ow = __shfl_sync(0xffffffffu, w, own);
+    const uint32_t oy0 = __shfl_sync(0xffffffffu, y0, own);
+    const uint32_t k = e - os;
+    const uint32_t ry = k / ow, rx = k - ry * ow;
+    if (act) {
+      tile_keys[e] = (oy0 + ry * (uint32_t)shard_count) * (uint32_t)grid_x + ox0 + rx;
+      gauss_vals[e] = og;
     }
   }
 }

@@ -95,26 +95,23 @@ blend_fwd_kernel(GcrBlendArgs a) {
           mask &= mask - 1;
           const float4 r0 = st[jj].q0;   // x, y, A, B   (broadcast LDS.128)
           const float4 r1 = st[jj].q1;   // C, o, r, g
-          const float cb = st[jj].q2.x;  // b
-          if (!done) {
-            const float dx = __fsub_rn(r0.x, pxf);
-            const float dy = __fsub_rn(r0.y, pyf);
-            const float power = gcr_power(dx, dy, r0.z, r0.w, r1.x);
-            if (!(power > 0.0f)) {
-              const float alpha = fminf(0.99f, __fmul_rn(r1.y, expf(power)));
-              if (!(alpha < 1.0f / 255.0f)) {
-                const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
-                if (test_T < 0.0001f) {
-                  done = true;
-                } else {
-                  C0 = __fmaf_rn(T, __fmul_rn(alpha, r1.z), C0);
-                  C1 = __fmaf_rn(T, __fmul_rn(alpha, r1.w), C1);
-                  C2 = __fmaf_rn(T, __fmul_rn(alpha, cb), C2);
-                  T = test_T;
-                  last_contributor = (uint32_t)(b * kBlendBatch + jj + 1);
-                }
-              }
-            }
+          // straight-line evaluation, state updates predicated: same arithmetic as the reference
+          // on every contributing lane, no per-test branches (the warp is issue-bound)
+          const float dx = __fsub_rn(r0.x, pxf);
+          const float dy = __fsub_rn(r0.y, pyf);
+          const float power = gcr_power(dx, dy, r0.z, r0.w, r1.x);
+          const float alpha = fminf(0.99f, __fmul_rn(r1.y, expf(power)));
+          const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+          const bool ok = !done && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+          const bool sat = ok && (test_T < 0.0001f);
+          done = done || sat;
+          if (ok && !sat) {
+            const float cb = st[jj].q2.x;  // b
+            C0 = __fmaf_rn(T, __fmul_rn(alpha, r1.z), C0);
+            C1 = __fmaf_rn(T, __fmul_rn(alpha, r1.w), C1);
+            C2 = __fmaf_rn(T, __fmul_rn(alpha, cb), C2);
+            T = test_T;
+            last_contributor = (uint32_t)(b * kBlendBatch + jj + 1);
           }
         }
         if (__ballot_sync(0xffffffffu, !done) == 0u) break;  // warp saturated
