@@ -406,37 +406,32 @@ blend_bwd_kernel_v2(GcrBlendArgs a) {
           const float4 r0 = st[jj].q0;
           const float4 r1 = st[jj].q1;
           const float cb = st[jj].q2.x;
+          // straight-line evaluation (the warp is issue-bound: no per-test branches); the
+          // per-pixel recurrences are only committed on contributing lanes
+          const float dx = __fsub_rn(r0.x, pxf);
+          const float dy = __fsub_rn(r0.y, pyf);
+          const float power = gcr_power(dx, dy, r0.z, r0.w, r1.x);
+          const float G = expf(power);
+          const float alpha = fminf(0.99f, __fmul_rn(r1.y, G));
+          // reference: contributor-- ; if (contributor >= last_contributor) continue; power > 0 and
+          // alpha < 1/255 skip as well
+          const bool contrib = (lo + jj < last_contributor) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
           float wA = 0.f, wB = 0.f, wG = 0.f;
-          bool contrib = false;
-          if (lo + jj < last_contributor) {
-            const float dx = __fsub_rn(r0.x, pxf);
-            const float dy = __fsub_rn(r0.y, pyf);
-            const float power = gcr_power(dx, dy, r0.z, r0.w, r1.x);
-            if (!(power > 0.0f)) {
-              const float G = expf(power);
-              const float alpha = fminf(0.99f, __fmul_rn(r1.y, G));
-              if (!(alpha < 1.0f / 255.0f)) {
-                contrib = true;
-                const float inv_1ma = __frcp_rn(1.f - alpha);
-                T = T * inv_1ma;
-                float dL_dalpha;
-                acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0;
-                lc0 = r1.z;
-                dL_dalpha = (r1.z - acc0) * dLp0;
-                acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1;
-                lc1 = r1.w;
-                dL_dalpha += (r1.w - acc1) * dLp1;
-                acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2;
-                lc2 = cb;
-                dL_dalpha += (cb - acc2) * dLp2;
-                dL_dalpha *= T;
-                last_alpha = alpha;
-                dL_dalpha += (-T_final * inv_1ma) * bg_dot_dpixel;
-                wA = alpha * T;
-                wB = dL_dalpha;
-                wG = G;
-              }
-            }
+          if (contrib) {
+            const float inv_1ma = __frcp_rn(1.f - alpha);
+            T = T * inv_1ma;
+            const float one_m_la = 1.f - last_alpha;
+            acc0 = fmaf(last_alpha, lc0, one_m_la * acc0);
+            acc1 = fmaf(last_alpha, lc1, one_m_la * acc1);
+            acc2 = fmaf(last_alpha, lc2, one_m_la * acc2);
+            lc0 = r1.z; lc1 = r1.w; lc2 = cb;
+            float dL_dalpha = (r1.z - acc0) * dLp0;
+            dL_dalpha = fmaf(r1.w - acc1, dLp1, dL_dalpha);
+            dL_dalpha = fmaf(cb - acc2, dLp2, dL_dalpha);
+            last_alpha = alpha;
+            wB = fmaf(dL_dalpha, T, (-T_final * inv_1ma) * bg_dot_dpixel);
+            wA = alpha * T;
+            wG = G;
           }
           if (__ballot_sync(0xffffffffu, contrib) != 0u) {
             panel[(0 * kSlots + nslot) * kPanelStride + lane] = wA;
