@@ -200,7 +200,7 @@ def run_gpu_arm(args, impl, rank, world, device):
             sets = [inp, {k: (v.clone() if k in big and v.numel() else v) for k, v in inp.items()}]
             st = {"i": 0, "h": None}
 
-            def step():
+            def step_broadcast():
                 i = st["i"]
                 if st["h"] is None and i == 0:
                     st["h"] = eng.start_prefetch(sets[0], src=0)
@@ -209,12 +209,17 @@ def run_gpu_arm(args, impl, rank, world, device):
                 out = eng.forward_backward_prefetched(s, sets[i % 2], grad_out)
                 st["i"], st["h"] = i + 1, nxt
                 return out
-            fwd_only = lambda: eng.forward(s, inp, src=0)
+
+            def step_replicated():
+                return eng.forward_backward_prefetched(s, inp, grad_out)
+            replicated = args.shard_mode == "replicated"
+            step = step_replicated if replicated else step_broadcast
+            fwd_only = (lambda: eng.render(inp, eng._cam(s, inp), broadcast=False)) if replicated else (lambda: eng.forward(s, inp, src=0))
             ms = max_over_ranks(time_steps(step, args.steps, args.warmup, barrier), device, world)
             ms_fwd = max_over_ranks(time_steps(fwd_only, max(2, args.steps // 2), 1, barrier), device, world)
             R = eng.last_num_rendered_total
             return dict(ms=ms, ms_fwd=ms_fwd, R=R, V=None, stages=None, P=P, W=W, H=H, s=s, inp=inp,
-                        grad_out=grad_out, extra={"parallelism": f"tile-row shard x{world}: NCCL broadcast of all Gaussian buffers every frame (prefetched one frame ahead on a side stream), image all_reduce, [P,12] reduce_scatter, per-slice geometry backward"})
+                        grad_out=grad_out, extra={"parallelism": (f"tile-row shard x{world}, Gaussians resident on every rank (no per-frame broadcast): image all_reduce, [P,12] reduce_scatter, per-slice geometry backward" if replicated else f"tile-row shard x{world}: NCCL broadcast of all Gaussian buffers every frame (prefetched one frame ahead on a side stream), image all_reduce, [P,12] reduce_scatter, per-slice geometry backward")})
         mod = ext
     else:
         from tests import refext
@@ -341,6 +346,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default=DEFAULT_WORKLOAD)
+    ap.add_argument("--shard-mode", choices=["broadcast", "replicated"], default="replicated",
+                    help="N>1: 'replicated' (default; consistent with `value` = inputs resident in HBM) = "
+                         "every rank holds the Gaussians, the exchange is the image all_reduce + the [P,12] "
+                         "gradient reduce_scatter; 'broadcast' = rank 0 owns them and NCCL-broadcasts all "
+                         "buffers every frame (1.18 GB at the default workload: NVLink-bound, see DESIGN.md 5)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
