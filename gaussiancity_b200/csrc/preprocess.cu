@@ -211,31 +211,65 @@ preprocess_fwd_kernel(GcrPreprocessArgs a) {
               if (k < nfl) sh[k] = __ldg(shf + k);
           }
 #define SHC(k, ch) sh[3 * (k) + (ch)]
+          // Basis scalars and the accumulation chain are pinned to the contraction nvcc emits for
+          // the reference's glm::vec3 expression (decoded from its SASS, forward.cu:20-66): every
+          // basis scalar is built with plain mul/add except 3xx-yy, 4zz-xx, 2zz-3xx-3yy, xx-3yy
+          // (fma), then res = fma(scalar, sh[k], res) in coefficient order.
+          float s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f, s5 = 0.f, s6 = 0.f, s7 = 0.f, s8 = 0.f;
+          float s9 = 0.f, s10 = 0.f, s11 = 0.f, s12 = 0.f, s13 = 0.f, s14 = 0.f, s15 = 0.f;
+          if (a.D > 0) {
+            s1 = __fmul_rn(y, GCR_SH_C1);
+            s2 = __fmul_rn(z, GCR_SH_C1);
+            s3 = __fmul_rn(x, GCR_SH_C1);
+            if (a.D > 1) {
+              const float xy = __fmul_rn(y, x), zy = __fmul_rn(z, y), zx = __fmul_rn(z, x);
+              const float zz = __fmul_rn(z, z), xx = __fmul_rn(x, x), yy = __fmul_rn(y, y);
+              const float zz2 = __fadd_rn(zz, zz);
+              const float xx_yy = __fsub_rn(xx, yy);
+              s4 = __fmul_rn(xy, GCR_SH_C2[0]);
+              s5 = __fmul_rn(zy, GCR_SH_C2[1]);
+              s6 = __fmul_rn(__fsub_rn(__fsub_rn(zz2, xx), yy), GCR_SH_C2[2]);
+              s7 = __fmul_rn(zx, GCR_SH_C2[3]);
+              s8 = __fmul_rn(xx_yy, GCR_SH_C2[4]);
+              if (a.D > 2) {
+                const float q = __fsub_rn(__fmaf_rn(zz, 4.0f, -xx), yy);                 // 4zz - xx - yy
+                const float u = __fmaf_rn(yy, -3.0f, __fmaf_rn(xx, -3.0f, zz2));          // 2zz - 3xx - 3yy
+                s9 = __fmul_rn(__fmul_rn(y, GCR_SH_C3[0]), __fmaf_rn(xx, 3.0f, -yy));
+                s10 = __fmul_rn(__fmul_rn(xy, GCR_SH_C3[1]), z);
+                s11 = __fmul_rn(__fmul_rn(y, GCR_SH_C3[2]), q);
+                s12 = __fmul_rn(__fmul_rn(z, GCR_SH_C3[3]), u);
+                s13 = __fmul_rn(q, __fmul_rn(x, GCR_SH_C3[4]));
+                s14 = __fmul_rn(xx_yy, __fmul_rn(z, GCR_SH_C3[5]));
+                s15 = __fmul_rn(__fmul_rn(x, GCR_SH_C3[6]), __fmaf_rn(yy, -3.0f, xx));
+              }
+            }
+          }
           float res[3];
 #pragma unroll
           for (int ch = 0; ch < 3; ++ch) {
-            float v = GCR_SH_C0 * SHC(0, ch);
+            float v = __fmul_rn(GCR_SH_C0, SHC(0, ch));
             if (a.D > 0) {
-              v = v - GCR_SH_C1 * y * SHC(1, ch) + GCR_SH_C1 * z * SHC(2, ch) -
-                  GCR_SH_C1 * x * SHC(3, ch);
+              v = __fmaf_rn(-s1, SHC(1, ch), v);
+              v = __fmaf_rn(s2, SHC(2, ch), v);
+              v = __fmaf_rn(-s3, SHC(3, ch), v);
               if (a.D > 1) {
-                const float xx = x * x, yy = y * y, zz = z * z;
-                const float xy = x * y, yz = y * z, xz = x * z;
-                v = v + GCR_SH_C2[0] * xy * SHC(4, ch) + GCR_SH_C2[1] * yz * SHC(5, ch) +
-                    GCR_SH_C2[2] * (2.0f * zz - xx - yy) * SHC(6, ch) +
-                    GCR_SH_C2[3] * xz * SHC(7, ch) + GCR_SH_C2[4] * (xx - yy) * SHC(8, ch);
+                v = __fmaf_rn(s4, SHC(4, ch), v);
+                v = __fmaf_rn(s5, SHC(5, ch), v);
+                v = __fmaf_rn(s6, SHC(6, ch), v);
+                v = __fmaf_rn(s7, SHC(7, ch), v);
+                v = __fmaf_rn(s8, SHC(8, ch), v);
                 if (a.D > 2) {
-                  v = v + GCR_SH_C3[0] * y * (3.0f * xx - yy) * SHC(9, ch) +
-                      GCR_SH_C3[1] * xy * z * SHC(10, ch) +
-                      GCR_SH_C3[2] * y * (4.0f * zz - xx - yy) * SHC(11, ch) +
-                      GCR_SH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * SHC(12, ch) +
-                      GCR_SH_C3[4] * x * (4.0f * zz - xx - yy) * SHC(13, ch) +
-                      GCR_SH_C3[5] * z * (xx - yy) * SHC(14, ch) +
-                      GCR_SH_C3[6] * x * (xx - 3.0f * yy) * SHC(15, ch);
+                  v = __fmaf_rn(s9, SHC(9, ch), v);
+                  v = __fmaf_rn(s10, SHC(10, ch), v);
+                  v = __fmaf_rn(s11, SHC(11, ch), v);
+                  v = __fmaf_rn(s12, SHC(12, ch), v);
+                  v = __fmaf_rn(s13, SHC(13, ch), v);
+                  v = __fmaf_rn(s14, SHC(14, ch), v);
+                  v = __fmaf_rn(s15, SHC(15, ch), v);
                 }
               }
             }
-            res[ch] = v + 0.5f;
+            res[ch] = __fadd_rn(v, 0.5f);
           }
 #undef SHC
           const uint8_t cl = (res[0] < 0 ? 1 : 0) | (res[1] < 0 ? 2 : 0) | (res[2] < 0 ? 4 : 0);

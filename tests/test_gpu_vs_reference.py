@@ -3,8 +3,9 @@
 
 Bars: bit-exact on integer tile/key work (radii, tiles_touched,
 num_rendered, sorted keys, point_list, ranges, n_contrib) -- and, because the arithmetic that
-feeds it is pinned, on mean2D / conic / depth / final_T too; <= 1e-4 relative on colours and on
-every gradient tensor (norm-relative, the reference's own atomics are order-nondeterministic).
+feeds it is pinned, on mean2D / conic / depth / final_T / per-Gaussian rgb / the rendered image too
+(the contract only asks <= 1e-4 on colours); <= 1e-4 norm-relative on every gradient tensor (the
+reference's own atomics are order-nondeterministic).
 """
 import pytest
 import torch
@@ -61,14 +62,13 @@ def test_forward_backward_match_reference(ref, built_lib, cuda_device, name, P, 
     assert torch.equal(rec[vis][:, 2:4], gv["conic_opacity"][vis][:, 0:2]), "conic.xy not bit-exact"
     assert torch.equal(rec[vis][:, 4:6], gv["conic_opacity"][vis][:, 2:4]), "conic.z/opacity not bit-exact"
     col_src = gv["rgb"] if use_sh else s.colors_precomp
-    rgb_err = (rec[vis][:, 6:9] - col_src[vis]).abs().max().item()
-    assert rgb_err <= 1e-5, f"per-Gaussian rgb differs by {rgb_err}"
+    # SH evaluation is pinned to the reference's contraction order too: colours are bit-exact
+    assert torch.equal(rec[vis][:, 6:9], col_src[vis]), \
+        f"per-Gaussian rgb differs at {(rec[vis][:, 6:9] != col_src[vis]).sum().item()} elements"
     if use_sh:
         cl = ov["clamped"][vis]
         cl3 = torch.stack([(cl & 1) != 0, (cl & 2) != 0, (cl & 4) != 0], dim=1)
-        # clamp flags may only differ where the colour sits within rounding of zero
-        diff = cl3 != gv["clamped"][vis]
-        assert diff.sum().item() <= max(2, int(1e-5 * P)), f"{diff.sum().item()} clamp flags differ"
+        assert torch.equal(cl3, gv["clamped"][vis]), "SH clamp flags differ"
 
     if R > 0:
         bv = refext.ref_binning_views(bin_ref, R)
@@ -84,11 +84,10 @@ def test_forward_backward_match_reference(ref, built_lib, cuda_device, name, P, 
     assert torch.equal(ov["final_T"], iv["accum_alpha"]), \
         f"final_T differs at {(ov['final_T'] != iv['accum_alpha']).sum().item()} pixels"
 
-    # ---- colour: <= 1e-4 relative (expected bit-exact) ----
+    # ---- colour: contract says <= 1e-4 relative; the pinned arithmetic makes it bit-exact ----
     nbad = (col != col_ref).sum().item()
-    assert torch.allclose(col, col_ref, rtol=1e-4, atol=1e-6), \
-        f"colour max abs err {(col - col_ref).abs().max().item()}"
-    print(f"[{name}] R={R} colour bitwise-different elements: {nbad}")
+    assert nbad == 0, f"colour differs at {nbad} elements, max abs err {(col - col_ref).abs().max().item()}"
+    print(f"[{name}] R={R} colour bit-exact")
 
     # ---- backward: norm-relative 1e-4 per tensor ----
     g = torch.Generator(device="cpu").manual_seed(seed + 100)
