@@ -465,11 +465,13 @@ void gcr_launch_blend_bwd(const GcrBlendArgs& a, cudaStream_t stream) {
     blend_bwd_kernel<<<grid, kBlendThreads, 0, stream>>>(a);
     return;
   }
-  static const bool configured = [] {
+  static bool configured[64] = {};   // the opt-in shared-memory size is a per-device attribute
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
     cudaFuncSetAttribute(blend_bwd_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          kBwdV2SmemBytes);
-    return true;
-  }();
-  (void)configured;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
   blend_bwd_kernel_v2<<<grid, kBlendThreads, kBwdV2SmemBytes, stream>>>(a);
 }

@@ -132,6 +132,8 @@ __forceinline__ __device__ float4 gcr_ldg_nc_f4(const float4* p) {
 // 256-bit global accesses (sm_100+: LDG.E.ENL2.256 / STG.E.ENL2.256): one full 32-byte sector
 // per thread per instruction; addr must be 32 B aligned.
 __forceinline__ __device__ void gcr_ldg_nc_v8(const float* p, float (&v)[8]) {
+  // volatile: keeps the loads where they are written (up front); without it the compiler sinks
+  // them next to their uses and the streaming kernels lose their memory-level parallelism
   asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]),
                  "=f"(v[7])

@@ -40,7 +40,7 @@ __forceinline__ __device__ int owned_rows(int y0, int y1, int rank, int count) {
 }
 
 template <bool kHasSH>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)   // <= 85 registers: 3 CTAs/SM for this streaming kernel
 preprocess_fwd_kernel(GcrPreprocessArgs a) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= a.P) return;

@@ -244,6 +244,8 @@ preprocess_bwd_kernel(GcrPreprocessBwdArgs a) {
         // 32-byte accesses (M = 16): every thread reads/writes whole sectors
         const float* __restrict__ shp = a.shs + shbase;
         float* __restrict__ dshp = a.dL_dsh + shbase;
+        // one sector at a time (load -> 8 outputs -> store): measured faster than issuing all six
+        // loads first, which costs 176 registers and drops the kernel to one CTA per SM
 #pragma unroll
         for (int q = 0; q < 6; ++q) {
           if (8 * q < nfl) {

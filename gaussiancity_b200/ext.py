@@ -82,7 +82,10 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
     P, H, W = int(means3D.size(0)), int(image_height), int(image_width)
 
     with torch.cuda.device(device):
-        out_color = torch.zeros((NUM_CHANNELS, H, W), dtype=torch.float32, device=device)
+        # every pixel is written by the blend when all tile rows are rendered; a tile-row shard
+        # leaves the other ranks' rows untouched, so those must start at zero
+        out_alloc = torch.empty if (int(shard_count) == 1 and P != 0) else torch.zeros
+        out_color = out_alloc((NUM_CHANNELS, H, W), dtype=torch.float32, device=device)
         radii = torch.zeros((P,), dtype=torch.int32, device=device)
         geom, binning, img = _Allocator(device), _Allocator(device), _Allocator(device)
         rendered = 0
