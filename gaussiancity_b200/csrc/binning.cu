@@ -382,6 +382,8 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
       *mine = kFlagIncl | acc;
     } else {
       *mine = kFlagAgg | acc;
+      // (an 8-wide batched walk was measured: no faster -- the wait is for predecessors to
+      // publish, not for the L2 round trips of the walk itself)
       long long t = (long long)tile - 1;
       while (true) {
         const uint32_t v = status[(size_t)t * kBins + tid];
@@ -431,7 +433,8 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
 // Small inputs (GaussianCity's own regime: P <= 16 384 points per frame, R of a few 10^4):
 // the multi-kernel sort above is launch-latency bound (3 launches per digit pass), so all digit
 // passes run inside ONE single-CTA kernel: 32 warps, chunks of 16 384 items, the same stable
-// match-any ranking, ping-pong through global memory (L2 resident at this size).
+// peer-mask ranking, ping-pong through global memory (L2 resident at this size).
+// MEASURED SLOWER than the multi-block path on B200 -> disabled by default (see below).
 // ------------------------------------------------------------------------------------------
 constexpr int kSmallThreads = 1024;
 constexpr int kSmallWarps = kSmallThreads / 32;

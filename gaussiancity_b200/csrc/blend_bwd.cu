@@ -8,11 +8,14 @@
 //
 // B200 design: same TMA-staged 2-stage ring as the forward (batches taken from the END of
 // the tile's contiguous record slice), same per-warp sub-rectangle cull, records beyond the
-// warp's furthest last-contributor are never touched.  Per surviving record the 9 partial
-// gradients are reduced across the warp's 32 pixels with shuffles and leave the SM as three
-// 16-byte vector reductions (red.global.add.v4.f32 -> REDG.E.ADD.F32x4) from one lane into a
-// 48-byte per-Gaussian accumulator: 3 L2 reduction ops per (warp, Gaussian) instead of
-// 9 x (number of contributing pixels).
+// CTA's furthest last-contributor are never staged.  Two kernels:
+//   blend_bwd_kernel_v2 (default): transposed reduction -- phase A (lane = pixel) parks three
+//     scalars per (record, pixel) in a warp-private shared-memory panel, phase B (lane = record
+//     x pixel row) accumulates the 9 gradient terms per record in registers and emits two
+//     16-byte vector reductions (red.global.add.v4.f32 -> REDG.E.ADD.F32x4) + one scalar.
+//   blend_bwd_kernel (GCR_BLEND_BWD=v1): per record, a value-halving shuffle butterfly
+//     (8 values in 9 shuffles + 1 in 5) and one predicated RED.ADD.F32 from 9 lanes.
+// Both write into the 48-byte per-Gaussian accumulator GcrGradAcc.
 #include <cstdlib>
 
 #include "blend_common.cuh"

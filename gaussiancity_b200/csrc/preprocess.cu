@@ -27,9 +27,6 @@ __forceinline__ __device__ float xf3(const float* __restrict__ m, int k, float x
   return __fmaf_rn(z, m[8 + k], __fmaf_rn(x, m[k], __fmul_rn(y, m[4 + k])));
 }
 
-struct ShardInfo {
-  int rank, count;
-};
 // number of tile rows r in [y0, y1) with r % count == rank
 __forceinline__ __device__ int owned_rows(int y0, int y1, int rank, int count) {
   if (count <= 1) return y1 - y0;
