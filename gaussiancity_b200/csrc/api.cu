@@ -205,6 +205,16 @@ int gcr_rasterizer_forward(gcr_alloc_fn geometryBuffer, void* geometry_ctx,
     return fail("SH degree does not fit the coefficient count");
   if (geometryBuffer == nullptr || binningBuffer == nullptr || imageBuffer == nullptr)
     return fail("buffer callbacks must not be NULL");
+  if (means3D == nullptr || opacities == nullptr || viewmatrix == nullptr || projmatrix == nullptr ||
+      background == nullptr || out_color == nullptr)
+    return fail("means3D, opacities, viewmatrix, projmatrix, background and out_color must not be NULL");
+  if (colors_precomp == nullptr && cam_pos == nullptr) return fail("cam_pos must not be NULL with SHs");
+  // vector loads: rotations are read as float4, SH rows as 32-byte (M = 16) or 16-byte words
+  if (rotations != nullptr && (reinterpret_cast<uintptr_t>(rotations) & 15u) != 0)
+    return fail("rotations must be 16-byte aligned");
+  if (colors_precomp == nullptr && ((M * 3) % 4) == 0 &&
+      (reinterpret_cast<uintptr_t>(shs) & (((M * 3) % 8) == 0 ? 31u : 15u)) != 0)
+    return fail("shs must be 32-byte aligned (16-byte when 3*M is not a multiple of 8)");
 
   const int grid_x = (width + GCR_TILE_X - 1) / GCR_TILE_X;
   const int grid_y = (height + GCR_TILE_Y - 1) / GCR_TILE_Y;
@@ -386,6 +396,13 @@ int gcr_rasterizer_backward_geometry(int P, int D, int M, const float* means3D, 
   if (cov3D_precomp == nullptr && (scales == nullptr || rotations == nullptr))
     return fail("provide either scale/rotation or a precomputed 3D covariance");
   if (shs != nullptr && M > 0 && dL_dsh == nullptr) return fail("dL_dsh must not be NULL with SHs");
+  if (rotations != nullptr && (reinterpret_cast<uintptr_t>(rotations) & 15u) != 0)
+    return fail("rotations must be 16-byte aligned");
+  if (shs != nullptr && M > 0 && ((M * 3) % 4) == 0) {
+    const uintptr_t mask = ((M * 3) % 8) == 0 ? 31u : 15u;
+    if ((reinterpret_cast<uintptr_t>(shs) & mask) != 0 || (reinterpret_cast<uintptr_t>(dL_dsh) & mask) != 0)
+      return fail("shs / dL_dsh must be 32-byte aligned (16-byte when 3*M is not a multiple of 8)");
+  }
   const GeomLayout gl((size_t)P);
   char* gptr = align256(geom_buffer);
   GcrPreprocessBwdArgs a;

@@ -53,3 +53,32 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_cabi, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_cabi.GcrLibraryError, match="no CPU fallback"):
         _cabi.lib()
+
+
+def test_argument_validation_returns_errors_without_touching_the_device(built_lib):
+    """Bad arguments are rejected before any CUDA call: safe to exercise on a GPU-less box."""
+    import ctypes as C
+    from gaussiancity_b200 import _cabi
+    l = _cabi.lib()
+    cb = _cabi.ALLOC_FN(lambda ctx, n: 0)
+    P = C.c_void_p
+    good = C.c_void_p(0x10000)   # never dereferenced on the host
+
+    def fwd(**kw):
+        a = dict(geom=cb, binning=cb, img=cb, P=4, D=0, M=1, bg=good, W=16, H=16, means=good, shs=good,
+                 colors=None, opac=good, scales=good, rot=good, cov=None, view=good, proj=good, campos=good,
+                 out=good, radii=None, shard_rank=0, shard_count=1)
+        a.update(kw)
+        return l.gcr_rasterizer_forward(a["geom"], None, a["binning"], None, a["img"], None, a["P"], a["D"], a["M"],
+                                        a["bg"], a["W"], a["H"], a["means"], a["shs"], a["colors"], a["opac"],
+                                        a["scales"], 1.0, a["rot"], a["cov"], a["view"], a["proj"], a["campos"],
+                                        1.0, 1.0, 0, a["out"], a["radii"], 0, a["shard_rank"], a["shard_count"], None)
+
+    assert fwd(P=0) == 0                                     # empty input: nothing to do
+    cases = [(dict(W=0), "image size"), (dict(shard_rank=2, shard_count=2), "shard"),
+             (dict(shs=None, colors=None), "SHs or precomputed"), (dict(scales=None), "scale/rotation"),
+             (dict(D=3, M=4), "SH degree"), (dict(rot=C.c_void_p(0x10004)), "16-byte aligned"),
+             (dict(M=16, D=3, shs=C.c_void_p(0x10010)), "32-byte aligned"), (dict(means=None), "must not be NULL")]
+    for kw, msg in cases:
+        assert fwd(**kw) < 0, kw
+        assert msg in _cabi.last_error(), (kw, _cabi.last_error())
