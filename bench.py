@@ -117,8 +117,10 @@ def tile_sort_passes(W, H):
 
 
 def kernels_per_step(W, H, backward=True):
-    """Kernels of OUR library launched by one forward(+backward) (memsets excluded)."""
-    fwd = 1 + 4 * 3 + 3 + 1 + tile_sort_passes(W, H) * 3 + 1 + 1
+    """Kernels of OUR library launched by one forward(+backward) (memsets excluded):
+    preprocess, depth sort (1 histogram + 4 onesweep passes), scan (3), emit, tile sort
+    (1 histogram + passes), ranges+gather, blend_fwd [+ blend_bwd, geometry_bwd]."""
+    fwd = 1 + (1 + 4) + 3 + 1 + (1 + tile_sort_passes(W, H)) + 1 + 1
     return fwd + (2 if backward else 0)
 
 
@@ -218,8 +220,33 @@ def run_gpu_arm(args, impl, rank, world, device):
             ms = max_over_ranks(time_steps(step, args.steps, args.warmup, barrier), device, world)
             ms_fwd = max_over_ranks(time_steps(fwd_only, max(2, args.steps // 2), 1, barrier), device, world)
             R = eng.last_num_rendered_total
+            # e2e at N GPUs: rank 0 copies every input from pinned host memory, NCCL-broadcasts
+            # it, all ranks render/backward their tile rows, rank 0 reads image + loss back
+            e2e = None
+            if not args.no_e2e:
+                big_keys = [k for k in big if inp[k].numel()]
+                host = {k: inp[k].cpu().pin_memory() for k in big_keys} if rank == 0 else {}
+                host_img = torch.empty(3, H, W, dtype=torch.float32).pin_memory()
+                host_loss = torch.empty(1, dtype=torch.float32).pin_memory()
+                cam = eng._cam(s, inp)
+
+                def step_e2e():
+                    if rank == 0:
+                        for k in big_keys:
+                            inp[k].copy_(host[k], non_blocking=True)
+                    eng.broadcast_gaussians({k: inp[k] for k in big_keys}, src=0)
+                    color, radii, state = eng.render(inp, cam, broadcast=False)
+                    eng.backward(state, inp, cam, grad_out)
+                    if rank == 0:
+                        host_img.copy_(color, non_blocking=True)
+                        host_loss.copy_((color * grad_out).sum().reshape(1), non_blocking=True)
+                ms_e = max_over_ranks(time_steps(step_e2e, max(2, args.steps // 2), 2, barrier), device, world)
+                h2d = sum(inp[k].numel() * 4 for k in big_keys)
+                e2e = {"value": P / (ms_e * 1e-3) / 1e6, "unit": "Msplats/s", "ms_per_step": ms_e,
+                       "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(host_img.numel() * 4 + 4),
+                       "note": "rank 0 H2D + NCCL broadcast of all inputs every step, tile-sharded fwd+bwd"}
             return dict(ms=ms, ms_fwd=ms_fwd, R=R, V=None, stages=None, P=P, W=W, H=H, s=s, inp=inp,
-                        grad_out=grad_out, extra={"parallelism": (f"tile-row shard x{world}, Gaussians resident on every rank (no per-frame broadcast): image all_reduce, [P,12] reduce_scatter, per-slice geometry backward" if replicated else f"tile-row shard x{world}: NCCL broadcast of all Gaussian buffers every frame (prefetched one frame ahead on a side stream), image all_reduce, [P,12] reduce_scatter, per-slice geometry backward")})
+                        grad_out=grad_out, e2e=e2e, extra={"parallelism": (f"tile-row shard x{world}, Gaussians resident on every rank (no per-frame broadcast): image all_reduce, [P,12] reduce_scatter, per-slice geometry backward" if replicated else f"tile-row shard x{world}: NCCL broadcast of all Gaussian buffers every frame (prefetched one frame ahead on a side stream), image all_reduce, [P,12] reduce_scatter, per-slice geometry backward")})
         mod = ext
     else:
         from tests import refext
@@ -417,7 +444,7 @@ def main():
                                     "sample": "full workload on the GPU: the reference has no CPU "
                                               "implementation of this path (SURVEY.md 8c)"}
         else:
-            line["gpu_launches"] = kernels_per_step(W, H) * args.steps if world_eff == 1 else None
+            line["gpu_launches"] = kernels_per_step(W, H) * args.steps   # per rank
             config.update(res["extra"])
             if world_eff == 1:
                 config["parallelism"] = "single GPU"
@@ -453,6 +480,8 @@ def main():
         e2e = run_e2e(args, args.impl, res, device)
         if rank == 0:
             line["e2e"] = e2e
+    elif world_eff > 1 and rank == 0 and res.get("e2e"):
+        line["e2e"] = res["e2e"]
     if rank == 0 and args.impl == "ours" and world_eff == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = run_cpu_baseline(args.workload)
     if rank == 0:
