@@ -313,32 +313,52 @@ radix_hist_all_kernel(const uint32_t* __restrict__ keys, size_t n, int end_bit,
     if (p < npass && hist[p][threadIdx.x] != 0) atomicAdd(&ghist[p * kBins + threadIdx.x], hist[p][threadIdx.x]);
 }
 
-template <bool kIota>
-__global__ void __launch_bounds__(kSortThreads, 4)
+// exclusive scan of one value per DIGIT (threads 0..255 carry values, any others pass 0)
+__device__ __forceinline__ uint32_t digit_excl_scan(uint32_t v, uint32_t* smem) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t inc = warp_incl_scan(v, lane);
+  if (lane == 31 && warp < 8) smem[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t w = (lane < 8) ? smem[lane] : 0;
+    const uint32_t winc = warp_incl_scan(w, lane);
+    if (lane < 8) smem[lane] = winc - w;
+  }
+  __syncthreads();
+  const uint32_t res = inc - v + ((warp < 8) ? smem[warp] : 0u);
+  __syncthreads();
+  return res;
+}
+
+// kThreads x 16 pairs per tile (4096 at 256 threads, 8192 at 512); all shared memory dynamic.
+template <bool kIota, int kThreads>
+__global__ void __launch_bounds__(kThreads, kThreads == 256 ? 4 : 2)
 onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                      uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, size_t n,
                      int shift, uint32_t digit_mask, int nbits,
                      const uint32_t* __restrict__ ghist_pass /* [kBins] */,
                      volatile uint32_t* status /* [tiles][kBins], zeroed */, uint32_t* ticket) {
-  __shared__ uint32_t warp_hist[8][kBins];
-  __shared__ uint32_t gbase[kBins];
-  __shared__ uint32_t bstart[kBins];
-  __shared__ uint32_t sm[16];
-  __shared__ uint32_t st_keys[kSortChunk];
-  __shared__ uint32_t st_vals[kSortChunk];
+  constexpr int kWarps = kThreads / 32;
+  constexpr int kTile = kThreads * kSortItems;
+  extern __shared__ __align__(16) uint32_t os_smem[];
+  uint32_t (*warp_hist)[kBins] = reinterpret_cast<uint32_t (*)[kBins]>(os_smem);
+  uint32_t* gbase = os_smem + kWarps * kBins;
+  uint32_t* bstart = gbase + kBins;
+  uint32_t* sm = bstart + kBins;          // 16 words
+  uint32_t* st_keys = sm + 16;
+  uint32_t* st_vals = st_keys + kTile;
   __shared__ uint32_t s_tile;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-#pragma unroll
-  for (int w = 0; w < 8; ++w) warp_hist[w][tid] = 0;
+  for (int i = tid; i < kWarps * kBins; i += kThreads) (&warp_hist[0][0])[i] = 0;
   __syncthreads();
   const uint32_t tile = s_tile;
 
-  const size_t chunk_base = (size_t)tile * kSortChunk;
+  const size_t chunk_base = (size_t)tile * kTile;
   const size_t base = chunk_base + (size_t)warp * (32 * kSortItems);
   // keys stay in registers across the ranking; values are fetched only when they are staged
-  // (keeps the kernel at <= 64 registers -> 4 CTAs/SM; it is bandwidth/latency bound)
+  // (keeps the kernel at <= 64 registers; it is bandwidth/latency bound)
   uint32_t key[kSortItems];
   uint16_t rank[kSortItems];
 #pragma unroll
@@ -365,37 +385,41 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
   __syncthreads();
 
   {
-    uint32_t acc = 0;   // this tile's count of digit `tid`
+    uint32_t acc = 0;   // this tile's count of digit `tid` (threads >= kBins idle here)
+    if (tid < kBins) {
 #pragma unroll
-    for (int w = 0; w < 8; ++w) {
-      const uint32_t t = warp_hist[w][tid];
-      warp_hist[w][tid] = acc;
-      acc += t;
-    }
-    uint32_t dummy;
-    bstart[tid] = block_excl_scan_256(acc, sm, &dummy);
-    const uint32_t dstart = block_excl_scan_256(ghist_pass[tid], sm, &dummy);
-    // decoupled look-back over the predecessors' status words for this digit
-    volatile uint32_t* mine = status + (size_t)tile * kBins + tid;
-    uint32_t excl = 0;
-    if (tile == 0) {
-      *mine = kFlagIncl | acc;
-    } else {
-      *mine = kFlagAgg | acc;
-      // (an 8-wide batched walk was measured: no faster -- the wait is for predecessors to
-      // publish, not for the L2 round trips of the walk itself)
-      long long t = (long long)tile - 1;
-      while (true) {
-        const uint32_t v = status[(size_t)t * kBins + tid];
-        const uint32_t f = v & ~kValMask;
-        if (f == 0u) continue;              // predecessor has not published yet: spin
-        excl += v & kValMask;
-        if (f == kFlagIncl) break;
-        --t;
+      for (int w = 0; w < kWarps; ++w) {
+        const uint32_t t = warp_hist[w][tid];
+        warp_hist[w][tid] = acc;
+        acc += t;
       }
-      *mine = kFlagIncl | (excl + acc);
     }
-    gbase[tid] = dstart + excl;
+    const uint32_t bs = digit_excl_scan(acc, sm);
+    const uint32_t dstart = digit_excl_scan(tid < kBins ? ghist_pass[tid] : 0u, sm);
+    if (tid < kBins) {
+      bstart[tid] = bs;
+      // decoupled look-back over the predecessors' status words for this digit
+      volatile uint32_t* mine = status + (size_t)tile * kBins + tid;
+      uint32_t excl = 0;
+      if (tile == 0) {
+        *mine = kFlagIncl | acc;
+      } else {
+        *mine = kFlagAgg | acc;
+        // (an 8-wide batched walk was measured: no faster -- the wait is for predecessors to
+        // publish, not for the L2 round trips of the walk itself)
+        long long t = (long long)tile - 1;
+        while (true) {
+          const uint32_t v = status[(size_t)t * kBins + tid];
+          const uint32_t f = v & ~kValMask;
+          if (f == 0u) continue;              // predecessor has not published yet: spin
+          excl += v & kValMask;
+          if (f == kFlagIncl) break;
+          --t;
+        }
+        *mine = kFlagIncl | (excl + acc);
+      }
+      gbase[tid] = dstart + excl;
+    }
   }
   __syncthreads();
 
@@ -419,14 +443,29 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
   }
   __syncthreads();
 
-  const uint32_t count = (uint32_t)min((size_t)kSortChunk, n - chunk_base);
-  for (uint32_t i = tid; i < count; i += kSortThreads) {
+  const uint32_t count = (uint32_t)min((size_t)kTile, n - chunk_base);
+  for (uint32_t i = tid; i < count; i += kThreads) {
     const uint32_t k = st_keys[i];
     const uint32_t d = (k >> shift) & digit_mask;
     const size_t dst = (size_t)gbase[d] + (i - bstart[d]);
     keys_out[dst] = k;
     vals_out[dst] = st_vals[i];
   }
+}
+
+template <bool kIota, int kThreads>
+void launch_onesweep_pass(unsigned tiles, cudaStream_t stream, const uint32_t* kin, const uint32_t* vin,
+                          uint32_t* kout, uint32_t* vout, size_t n, int shift, uint32_t mask, int bits,
+                          const uint32_t* ghist, uint32_t* st, uint32_t* ticket) {
+  constexpr int smem = ((kThreads / 32) * kBins + 2 * kBins + 16 + 2 * kThreads * kSortItems) * 4;
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    cudaFuncSetAttribute(onesweep_pass_kernel<kIota, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
+  onesweep_pass_kernel<kIota, kThreads><<<tiles, kThreads, smem, stream>>>(kin, vin, kout, vout, n, shift, mask, bits, ghist, st, ticket);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -770,6 +809,7 @@ int gcr_launch_radix_sort(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, 
     uint32_t* tickets = ws + kMaxPasses * kBins;
     uint32_t* status = ws + kMaxPasses * kBins + 64;
     const int npass = (end_bit + 7) / 8;
+    static const bool big_tiles = [] { const char* e = getenv("GCR_SORT_TILE"); return e != nullptr && atoi(e) >= 8192; }();
     cudaMemsetAsync(ws, 0, (kMaxPasses * kBins + 64 + (size_t)npass * nblk * kBins) * sizeof(uint32_t), stream);
     const unsigned hgrid = (unsigned)min((size_t)nblk, (size_t)148 * 8);
     radix_hist_all_kernel<<<hgrid, kSortThreads, 0, stream>>>(keys_a, n, end_bit, ghist);
@@ -779,10 +819,15 @@ int gcr_launch_radix_sort(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, 
       const int bits = min(8, end_bit - shift);
       const uint32_t mask = (1u << bits) - 1u;
       uint32_t* st = status + (size_t)p * nblk * kBins;
-      if (vals_iota && p == 0)
-        onesweep_pass_kernel<true><<<nblk, kSortThreads, 0, stream>>>(kin, vin, kout, vout, n, shift, mask, bits, ghist + p * kBins, st, tickets + p);
-      else
-        onesweep_pass_kernel<false><<<nblk, kSortThreads, 0, stream>>>(kin, vin, kout, vout, n, shift, mask, bits, ghist + p * kBins, st, tickets + p);
+      const bool iota = vals_iota && p == 0;
+      if (big_tiles) {
+        const unsigned tiles = (unsigned)((n + 8191) / 8192);
+        if (iota) launch_onesweep_pass<true, 512>(tiles, stream, kin, vin, kout, vout, n, shift, mask, bits, ghist + p * kBins, st, tickets + p);
+        else launch_onesweep_pass<false, 512>(tiles, stream, kin, vin, kout, vout, n, shift, mask, bits, ghist + p * kBins, st, tickets + p);
+      } else {
+        if (iota) launch_onesweep_pass<true, 256>(nblk, stream, kin, vin, kout, vout, n, shift, mask, bits, ghist + p * kBins, st, tickets + p);
+        else launch_onesweep_pass<false, 256>(nblk, stream, kin, vin, kout, vout, n, shift, mask, bits, ghist + p * kBins, st, tickets + p);
+      }
       uint32_t* t = kin; kin = kout; kout = t;
       t = vin; vin = vout; vout = t;
     }
