@@ -346,7 +346,7 @@ def run_cpu_baseline(workload, budget_s=20.0):
     from gaussiancity_b200.synthetic import uniform_scene
     from oracle import oracle as cpu_oracle
     P, W, H, deg, use_sh = WORKLOADS[workload]
-    n = min(P, 200_000)
+    n = min(P, 1_000_000)
     s = uniform_scene(n, W, H, sh_degree=deg, seed=0, device="cpu", use_sh=use_sh)
     G = np.random.default_rng(0).standard_normal((3, H, W)).astype(np.float32)
     cores = os.cpu_count() or 1
@@ -357,7 +357,7 @@ def run_cpu_baseline(workload, budget_s=20.0):
         r = cpu_oracle.forward_scene(s, "f32")
         cpu_oracle.backward(r, G)
         reps += 1
-        if time.time() - t0 > budget_s * 0.5 or reps >= 3:
+        if time.time() - t0 > budget_s * 0.5 or reps >= 6:
             break
     dt = (time.time() - t0) / reps
     return {"value": n / dt / 1e6, "unit": "Msplats/s", "cores": cores, "kind": "port",
