@@ -273,6 +273,7 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
 // traffic and 1 + passes launches per sort (was 20 B and 3 x passes).  Tiles are handed out by
 // an atomic ticket so a tile's predecessors have always started: the look-back cannot deadlock.
 // ------------------------------------------------------------------------------------------
+constexpr size_t kSmallTileMaxN = 262144;   // up to here the 1024-pair tiles are used
 constexpr uint32_t kFlagAgg = 1u << 30, kFlagIncl = 2u << 30, kValMask = (1u << 30) - 1u;
 constexpr int kMaxPasses = 4;
 
@@ -330,8 +331,10 @@ __device__ __forceinline__ uint32_t digit_excl_scan(uint32_t v, uint32_t* smem) 
   return res;
 }
 
-// kThreads x 16 pairs per tile (4096 at 256 threads, 8192 at 512); all shared memory dynamic.
-template <bool kIota, int kThreads>
+// kThreads x kItems pairs per tile (256 x 16 = 4096 by default; 256 x 4 = 1024 for small inputs,
+// where the 16 serial ranking rounds of a few lonely CTAs are the whole latency); all shared
+// memory dynamic.
+template <bool kIota, int kThreads, int kItems>
 __global__ void __launch_bounds__(kThreads, kThreads == 256 ? 4 : 2)
 onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                      uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, size_t n,
@@ -339,7 +342,7 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
                      const uint32_t* __restrict__ ghist_pass /* [kBins] */,
                      volatile uint32_t* status /* [tiles][kBins], zeroed */, uint32_t* ticket) {
   constexpr int kWarps = kThreads / 32;
-  constexpr int kTile = kThreads * kSortItems;
+  constexpr int kTile = kThreads * kItems;
   extern __shared__ __align__(16) uint32_t os_smem[];
   uint32_t (*warp_hist)[kBins] = reinterpret_cast<uint32_t (*)[kBins]>(os_smem);
   uint32_t* gbase = os_smem + kWarps * kBins;
@@ -356,18 +359,18 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
   const uint32_t tile = s_tile;
 
   const size_t chunk_base = (size_t)tile * kTile;
-  const size_t base = chunk_base + (size_t)warp * (32 * kSortItems);
+  const size_t base = chunk_base + (size_t)warp * (32 * kItems);
   // keys stay in registers across the ranking; values are fetched only when they are staged
   // (keeps the kernel at <= 64 registers; it is bandwidth/latency bound)
-  uint32_t key[kSortItems];
-  uint16_t rank[kSortItems];
+  uint32_t key[kItems];
+  uint16_t rank[kItems];
 #pragma unroll
-  for (int r = 0; r < kSortItems; ++r) {
+  for (int r = 0; r < kItems; ++r) {
     const size_t i = base + (size_t)r * 32 + lane;
     key[r] = i < n ? keys_in[i] : 0u;
   }
 #pragma unroll
-  for (int r = 0; r < kSortItems; ++r) {
+  for (int r = 0; r < kItems; ++r) {
     const size_t i = base + (size_t)r * 32 + lane;
     const bool valid = i < n;
     const unsigned vmask = __ballot_sync(0xffffffffu, valid);
@@ -424,14 +427,14 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
   __syncthreads();
 
   {
-    uint32_t val[kSortItems];
+    uint32_t val[kItems];
 #pragma unroll
-    for (int r = 0; r < kSortItems; ++r) {
+    for (int r = 0; r < kItems; ++r) {
       const size_t i = base + (size_t)r * 32 + lane;
       val[r] = kIota ? (uint32_t)i : (i < n ? vals_in[i] : 0u);
     }
 #pragma unroll
-    for (int r = 0; r < kSortItems; ++r) {
+    for (int r = 0; r < kItems; ++r) {
       const size_t i = base + (size_t)r * 32 + lane;
       if (i < n) {
         const uint32_t d = (key[r] >> shift) & digit_mask;
@@ -453,19 +456,19 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
   }
 }
 
-template <bool kIota, int kThreads>
+template <bool kIota, int kThreads, int kItems>
 void launch_onesweep_pass(unsigned tiles, cudaStream_t stream, const uint32_t* kin, const uint32_t* vin,
                           uint32_t* kout, uint32_t* vout, size_t n, int shift, uint32_t mask, int bits,
                           const uint32_t* ghist, uint32_t* st, uint32_t* ticket) {
-  constexpr int smem = ((kThreads / 32) * kBins + 2 * kBins + 16 + 2 * kThreads * kSortItems) * 4;
+  constexpr int smem = ((kThreads / 32) * kBins + 2 * kBins + 16 + 2 * kThreads * kItems) * 4;
   static bool configured[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !configured[dev]) {
-    cudaFuncSetAttribute(onesweep_pass_kernel<kIota, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(onesweep_pass_kernel<kIota, kThreads, kItems>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
-  onesweep_pass_kernel<kIota, kThreads><<<tiles, kThreads, smem, stream>>>(kin, vin, kout, vout, n, shift, mask, bits, ghist, st, ticket);
+  onesweep_pass_kernel<kIota, kThreads, kItems><<<tiles, kThreads, smem, stream>>>(kin, vin, kout, vout, n, shift, mask, bits, ghist, st, ticket);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -778,7 +781,9 @@ void gcr_launch_inclusive_scan(const uint32_t* in, const uint32_t* gather, uint3
 }
 
 size_t gcr_sort_workspace_bytes(size_t n) {
-  const size_t nblk = (n + kSortChunk - 1) / kSortChunk;
+  size_t nblk = (n + kSortChunk - 1) / kSortChunk;
+  const size_t small = (n + 1023) / 1024;   // 1024-pair tiles may be used (always when n is small, or by env)
+  if (small > nblk) nblk = small;
   // onesweep: global histograms [4][256] + tickets [4] (+pad) + status [4][nblk][256]
   return gcr_align_up((kMaxPasses * kBins + 64 + kMaxPasses * nblk * kBins) * sizeof(uint32_t), 256);
 }
@@ -809,8 +814,12 @@ int gcr_launch_radix_sort(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, 
     uint32_t* tickets = ws + kMaxPasses * kBins;
     uint32_t* status = ws + kMaxPasses * kBins + 64;
     const int npass = (end_bit + 7) / 8;
-    static const bool big_tiles = [] { const char* e = getenv("GCR_SORT_TILE"); return e != nullptr && atoi(e) >= 8192; }();
-    cudaMemsetAsync(ws, 0, (kMaxPasses * kBins + 64 + (size_t)npass * nblk * kBins) * sizeof(uint32_t), stream);
+    static const int tile_env = [] { const char* e = getenv("GCR_SORT_TILE"); return e ? atoi(e) : 0; }();
+    const bool big_tiles = tile_env >= 8192;
+    // small inputs: 1024-pair tiles (4 ranking rounds instead of 16) -- latency, not bandwidth
+    const bool small_tiles = (tile_env == 0 && n <= kSmallTileMaxN) || tile_env == 1024;
+    const size_t ntiles = small_tiles ? (n + 1023) / 1024 : nblk;   // status stride per pass
+    cudaMemsetAsync(ws, 0, (kMaxPasses * kBins + 64 + (size_t)npass * ntiles * kBins) * sizeof(uint32_t), stream);
     const unsigned hgrid = (unsigned)min((size_t)nblk, (size_t)148 * 8);
     radix_hist_all_kernel<<<hgrid, kSortThreads, 0, stream>>>(keys_a, n, end_bit, ghist);
     uint32_t* kin = keys_a; uint32_t* vin = vals_a; uint32_t* kout = keys_b; uint32_t* vout = vals_b;
@@ -818,15 +827,19 @@ int gcr_launch_radix_sort(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, 
       const int shift = 8 * p;
       const int bits = min(8, end_bit - shift);
       const uint32_t mask = (1u << bits) - 1u;
-      uint32_t* st = status + (size_t)p * nblk * kBins;
+      uint32_t* st = status + (size_t)p * ntiles * kBins;
       const bool iota = vals_iota && p == 0;
-      if (big_tiles) {
+      if (small_tiles) {
+        const unsigned tiles = (unsigned)((n + 1023) / 1024);
+        if (iota) launch_onesweep_pass<true, 256, 4>(tiles, stream, kin, vin, kout, vout, n, shift, mask, bits, ghist + p * kBins, st, tickets + p);
+        else launch_onesweep_pass<false, 256, 4>(tiles, stream, kin, vin, kout, vout, n, shift, mask, bits, ghist + p * kBins, st, tickets + p);
+      } else if (big_tiles) {
         const unsigned tiles = (unsigned)((n + 8191) / 8192);
-        if (iota) launch_onesweep_pass<true, 512>(tiles, stream, kin, vin, kout, vout, n, shift, mask, bits, ghist + p * kBins, st, tickets + p);
-        else launch_onesweep_pass<false, 512>(tiles, stream, kin, vin, kout, vout, n, shift, mask, bits, ghist + p * kBins, st, tickets + p);
+        if (iota) launch_onesweep_pass<true, 512, 16>(tiles, stream, kin, vin, kout, vout, n, shift, mask, bits, ghist + p * kBins, st, tickets + p);
+        else launch_onesweep_pass<false, 512, 16>(tiles, stream, kin, vin, kout, vout, n, shift, mask, bits, ghist + p * kBins, st, tickets + p);
       } else {
-        if (iota) launch_onesweep_pass<true, 256>(nblk, stream, kin, vin, kout, vout, n, shift, mask, bits, ghist + p * kBins, st, tickets + p);
-        else launch_onesweep_pass<false, 256>(nblk, stream, kin, vin, kout, vout, n, shift, mask, bits, ghist + p * kBins, st, tickets + p);
+        if (iota) launch_onesweep_pass<true, 256, 16>(nblk, stream, kin, vin, kout, vout, n, shift, mask, bits, ghist + p * kBins, st, tickets + p);
+        else launch_onesweep_pass<false, 256, 16>(nblk, stream, kin, vin, kout, vout, n, shift, mask, bits, ghist + p * kBins, st, tickets + p);
       }
       uint32_t* t = kin; kin = kout; kout = t;
       t = vin; vin = vout; vout = t;
