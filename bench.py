@@ -360,7 +360,22 @@ def run_cpu_baseline(workload, budget_s=20.0):
         if time.time() - t0 > budget_s * 0.5 or reps >= 6:
             break
     dt = (time.time() - t0) / reps
+    # BASELINE config 1 as worded in the north star: naive PyTorch per-pixel blend on the host CPU
+    # (1 k Gaussians -> 128x128, forward only). Reported next to the oracle port; never a target.
+    naive = None
+    try:
+        from oracle import torch_naive
+        torch.set_num_threads(cores)
+        s1 = uniform_scene(1000, 128, 128, sh_degree=3, seed=0, device="cpu")
+        t1 = time.time()
+        torch_naive.render_naive(s1)
+        d1 = time.time() - t1
+        naive = {"workload": "config 1: 1k Gaussians, SH 3, 128x128, forward only", "seconds": d1,
+                 "Msplats_per_s_forward": 1000 / d1 / 1e6, "MPix_per_s": 128 * 128 / d1 / 1e6}
+    except Exception as e:  # the reported baseline must never take the bench line down
+        naive = {"error": repr(e)[:200]}
     return {"value": n / dt / 1e6, "unit": "Msplats/s", "cores": cores, "kind": "port",
+            "torch_naive_config1": naive,
             "sample": f"first {n} Gaussians of {workload} at {W}x{H}, fwd+bwd, {reps} rep(s), "
                       f"{dt:.2f} s each (oracle/gs_oracle.c fp32; preprocess+sort serial, blend OpenMP)"}
 

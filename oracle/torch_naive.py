@@ -1,0 +1,118 @@
+"""Naive pure-PyTorch CPU restatement of the forward (BASELINE config 1: "1k synthetic Gaussians ->
+128x128, forward only, naive PyTorch CPU per-pixel blend").  TEST INFRASTRUCTURE / reported CPU
+baseline only -- never imported by gaussiancity_b200.
+
+Restates DGR/cuda_rasterizer/forward.cu:147-346 without tiles: per-Gaussian preprocessing is
+vectorised over Gaussians, then Gaussians are visited in (depth, index) order and every pixel is
+blended at once (a Python loop over Gaussians, tensor ops over the H x W pixels).  Without the tile
+bounding squares of the reference a splat also reaches pixels outside its 3-sigma square, so the
+per-pixel restriction to the reference's tile rectangle is applied explicitly (rect mask).
+fp32 throughout; SH degree 0-3 or precomputed colours.
+"""
+import math
+
+import torch
+
+C0 = 0.28209479177387814
+C1 = 0.4886025119029199
+C2 = (1.0925484305920792, -1.0925484305920792, 0.31539156525252005, -1.0925484305920792, 0.5462742152960396)
+C3 = (-0.5900435899266435, 2.890611442640554, -0.4570457994644658, 0.3731763325901154,
+      -0.4570457994644658, 1.445305721320277, -0.5900435899266435)
+
+
+def _sh_to_rgb(deg, shs, dirs):
+    x, y, z = dirs[:, 0:1], dirs[:, 1:2], dirs[:, 2:3]
+    res = C0 * shs[:, 0]
+    if deg > 0:
+        res = res - C1 * y * shs[:, 1] + C1 * z * shs[:, 2] - C1 * x * shs[:, 3]
+        if deg > 1:
+            xx, yy, zz, xy, yz, xz = x * x, y * y, z * z, x * y, y * z, x * z
+            res = (res + C2[0] * xy * shs[:, 4] + C2[1] * yz * shs[:, 5] + C2[2] * (2 * zz - xx - yy) * shs[:, 6]
+                   + C2[3] * xz * shs[:, 7] + C2[4] * (xx - yy) * shs[:, 8])
+            if deg > 2:
+                res = (res + C3[0] * y * (3 * xx - yy) * shs[:, 9] + C3[1] * xy * z * shs[:, 10]
+                       + C3[2] * y * (4 * zz - xx - yy) * shs[:, 11] + C3[3] * z * (2 * zz - 3 * xx - 3 * yy) * shs[:, 12]
+                       + C3[4] * x * (4 * zz - xx - yy) * shs[:, 13] + C3[5] * z * (xx - yy) * shs[:, 14]
+                       + C3[6] * x * (xx - 3 * yy) * shs[:, 15])
+    return torch.clamp_min(res + 0.5, 0.0)
+
+
+def render_naive(s):
+    """s: gaussiancity_b200.synthetic.Scene with CPU tensors -> (color[3,H,W], radii[P])."""
+    f32 = torch.float32
+    P, W, H = s.means3D.shape[0], s.img_w, s.img_h
+    V, PM = s.view_matrix.to(f32), s.proj_matrix.to(f32)     # transposed (row-vector) matrices
+    p = s.means3D.to(f32)
+    ph = torch.cat([p, torch.ones(P, 1)], dim=1)
+    view = ph @ V                                             # [P,4] camera space
+    hom = ph @ PM
+    pw = 1.0 / (hom[:, 3] + 1e-7)
+    ndc = hom[:, :2] * pw[:, None]
+    tz = view[:, 2]
+    visible = tz > 0.2
+    # 3D covariance  Sigma = R S^2 R^T with the UN-normalised quaternion (r, x, y, z)
+    q = s.rotations.to(f32)
+    r, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    R = torch.stack([
+        torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y)], dim=1),
+        torch.stack([2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x)], dim=1),
+        torch.stack([2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)], dim=1)], dim=1)
+    Sg = R @ torch.diag_embed(s.scales.to(f32) ** 2) @ R.transpose(1, 2)
+    # EWA projection
+    fx, fy = W / (2.0 * s.tanfovx), H / (2.0 * s.tanfovy)
+    limx, limy = 1.3 * s.tanfovx, 1.3 * s.tanfovy
+    tzs = torch.where(visible, tz, torch.ones_like(tz))
+    tx = torch.clamp(view[:, 0] / tzs, -limx, limx) * tzs
+    ty = torch.clamp(view[:, 1] / tzs, -limy, limy) * tzs
+    J = torch.zeros(P, 2, 3)
+    J[:, 0, 0], J[:, 0, 2] = fx / tzs, -fx * tx / (tzs * tzs)
+    J[:, 1, 1], J[:, 1, 2] = fy / tzs, -fy * ty / (tzs * tzs)
+    Rw = V[:3, :3].T                                          # world -> camera rotation
+    T = J @ Rw
+    cov = T @ Sg @ T.transpose(1, 2)
+    a, b, c = cov[:, 0, 0] + 0.3, cov[:, 0, 1], cov[:, 1, 1] + 0.3
+    det = a * c - b * b
+    ok = visible & (det != 0)
+    dets = torch.where(ok, det, torch.ones_like(det))
+    conic = torch.stack([c / dets, -b / dets, a / dets], dim=1)
+    mid = 0.5 * (a + c)
+    lam = mid + torch.sqrt(torch.clamp_min(mid * mid - det, 0.1))
+    radius = torch.ceil(3.0 * torch.sqrt(torch.where(ok, lam, torch.ones_like(lam))))
+    px = ((ndc[:, 0].double() + 1.0) * W - 1.0) * 0.5
+    py = ((ndc[:, 1].double() + 1.0) * H - 1.0) * 0.5
+    px, py = px.to(f32), py.to(f32)
+    gx, gy = (W + 15) // 16, (H + 15) // 16
+    x0 = torch.clamp(torch.trunc((px - radius) / 16), 0, gx)
+    y0 = torch.clamp(torch.trunc((py - radius) / 16), 0, gy)
+    x1 = torch.clamp(torch.trunc((px + radius + 15) / 16), 0, gx)
+    y1 = torch.clamp(torch.trunc((py + radius + 15) / 16), 0, gy)
+    ok = ok & ((x1 - x0) * (y1 - y0) > 0)
+    radii = torch.where(ok, radius, torch.zeros_like(radius)).to(torch.int32)
+    if s.colors_precomp is not None:
+        rgb = s.colors_precomp.to(f32)
+    else:
+        d = p - s.campos.to(f32)[None]
+        rgb = _sh_to_rgb(s.sh_degree, s.shs.to(f32), d / d.norm(dim=1, keepdim=True))
+    opac = s.opacities.to(f32).reshape(-1)
+    # front-to-back over Gaussians in (depth, index) order, all pixels at once
+    idx = torch.nonzero(ok).flatten()
+    order = idx[torch.sort(tz[idx], stable=True).indices]
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=f32), torch.arange(W, dtype=f32), indexing="ij")
+    Tr = torch.ones(H, W)
+    done = torch.zeros(H, W, dtype=torch.bool)
+    C = torch.zeros(3, H, W)
+    for g in order.tolist():
+        rx0, rx1, ry0, ry1 = int(x0[g]) * 16, int(x1[g]) * 16, int(y0[g]) * 16, int(y1[g]) * 16
+        sl = (slice(ry0, min(ry1, H)), slice(rx0, min(rx1, W)))       # the reference's tile rectangle
+        dx, dy = px[g] - xs[sl], py[g] - ys[sl]
+        power = -0.5 * (conic[g, 0] * dx * dx + conic[g, 2] * dy * dy) - conic[g, 1] * dx * dy
+        alpha = torch.clamp_max(opac[g] * torch.exp(power), 0.99)
+        contrib = (~done[sl]) & (power <= 0) & (alpha >= 1.0 / 255.0)
+        test_T = Tr[sl] * (1 - alpha)
+        sat = contrib & (test_T < 1e-4)
+        done[sl] |= sat
+        upd = contrib & ~sat
+        w = torch.where(upd, alpha * Tr[sl], torch.zeros_like(alpha))
+        C[:, sl[0], sl[1]] += rgb[g][:, None, None] * w[None]
+        Tr[sl] = torch.where(upd, test_T, Tr[sl])
+    return C + Tr[None] * s.bg.to(f32)[:, None, None], radii

@@ -121,3 +121,16 @@ def test_oracle_gradients_match_finite_differences():
             assert abs(fd - an) <= 2e-3 * max(abs(fd), abs(an)) + 1e-7, (key, fd, an)
     finally:
         oracle.set_smooth(False, "f64")
+
+
+@pytest.mark.parametrize("deg,use_sh", [(3, True), (1, True), (0, False)])
+def test_naive_torch_restatement_agrees_with_c_oracle(deg, use_sh):
+    """BASELINE config 1 (1k Gaussians -> 128x128, forward, naive PyTorch per-pixel blend): a third,
+    tile-free restatement of the forward must agree with the C oracle."""
+    from gaussiancity_b200.synthetic import uniform_scene
+    from oracle import torch_naive
+    s = uniform_scene(1000, 128, 128, sh_degree=deg, seed=deg, use_sh=use_sh, bg=(0.1, 0.2, 0.3))
+    col, radii = torch_naive.render_naive(s)
+    r = oracle.forward_scene(s, "f32")
+    assert (radii.numpy() != r.radii).sum() <= 1
+    assert np.abs(col.numpy() - r.color).max() < 5e-5
