@@ -134,3 +134,21 @@ def test_naive_torch_restatement_agrees_with_c_oracle(deg, use_sh):
     r = oracle.forward_scene(s, "f32")
     assert (radii.numpy() != r.radii).sum() <= 1
     assert np.abs(col.numpy() - r.color).max() < 5e-5
+
+
+def test_oracle_precomputed_covariance_and_scale_modifier_paths():
+    """The optional-input paths the GPU tests lean on: cov3D_precomp == covariance from
+    scale/rotation, and scale_modifier == pre-scaled scales."""
+    from gaussiancity_b200.synthetic import uniform_scene
+    s = uniform_scene(800, 96, 64, sh_degree=1, seed=17)
+    c = lambda t: t.numpy()
+    kw = dict(shs=c(s.shs), sh_degree=1, precision="f32")
+    args = (c(s.view_matrix), c(s.proj_matrix), c(s.campos), 96, 64, s.tanfovx, s.tanfovy, c(s.bg))
+    a = oracle.forward(c(s.means3D), c(s.opacities), c(s.scales), c(s.rotations), *args, **kw)
+    b = oracle.forward(c(s.means3D), c(s.opacities), None, None, *args, cov3D_precomp=a.cov3D, **kw)
+    assert np.array_equal(a.radii, b.radii) and np.array_equal(a.point_list, b.point_list)
+    assert np.array_equal(a.color, b.color)
+    m = oracle.forward(c(s.means3D), c(s.opacities), c(s.scales) * 0.5, c(s.rotations), *args, scale_modifier=2.0, **kw)
+    assert np.array_equal(m.radii, a.radii) and np.allclose(m.color, a.color, atol=1e-6)
+    g = oracle.backward(b, np.ones((3, 64, 96), np.float32))
+    assert np.all(g["dL_dscale"] == 0) and np.all(g["dL_drot"] == 0) and np.abs(g["dL_dcov3D"]).sum() > 0
