@@ -341,7 +341,7 @@ def run_e2e(args, impl, res, device):
 
 def run_cpu_baseline(workload, budget_s=20.0):
     """CPU oracle port (oracle/gs_oracle.c, OpenMP in the blend stages) on a bounded sample of
-    the same workload: the first `n` Gaussians at full resolution, forward + backward."""
+    the same workload: `n` Gaussians of the same distribution at full resolution, fwd + bwd."""
     import numpy as np
     from gaussiancity_b200.synthetic import uniform_scene
     from oracle import oracle as cpu_oracle
@@ -376,7 +376,7 @@ def run_cpu_baseline(workload, budget_s=20.0):
         naive = {"error": repr(e)[:200]}
     return {"value": n / dt / 1e6, "unit": "Msplats/s", "cores": cores, "kind": "port",
             "torch_naive_config1": naive,
-            "sample": f"first {n} Gaussians of {workload} at {W}x{H}, fwd+bwd, {reps} rep(s), "
+            "sample": f"{n} Gaussians from the distribution of {workload} at {W}x{H}, fwd+bwd, {reps} rep(s), "
                       f"{dt:.2f} s each (oracle/gs_oracle.c fp32; preprocess+sort serial, blend OpenMP)"}
 
 
