@@ -474,17 +474,28 @@ def main():
             dom = max(("blend_bwd", "blend_fwd"), key=lambda k: stages.get(k, 0.0))
             dur = stages[dom]
             achieved = alg[dom] / (dur * 1e-3) / 1e9
-            traffic = None
+            traffic, issue = None, None
             tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
             if os.path.exists(tpath):
                 with open(tpath) as fh:
                     tj = json.load(fh)
                 if tj.get("workload") == args.workload:   # per-launch DRAM bytes from the committed
-                    traffic = tj["kernels"].get(dom, {}).get("dram_bytes")   # ncu --set full capture
+                    kj = tj["kernels"].get(dom, {})       # ncu --set full capture
+                    traffic = kj.get("dram_bytes")
+                    winst = kj.get("warp_instructions")
+                    sm_mhz = (clocks or {}).get("sm_mhz")
+                    if winst and sm_mhz:
+                        # what actually binds the blend kernels: warp instructions issued (from the
+                        # same ncu capture) / live kernel time, against 148 SMs x 4 schedulers x
+                        # 1 instruction/clk at the SM clock sampled during this run
+                        ipeak = 148 * 4 * sm_mhz * 1e6
+                        iach = winst / (dur * 1e-3)
+                        issue = {"warp_instructions": winst, "achieved_ginst_s": iach / 1e9,
+                                 "peak_ginst_s": ipeak / 1e9, "frac": iach / ipeak}
             line["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak,
                                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                                 "peak_source": peak_src, "kernel_ms": dur,
-                                "algorithmic_bytes": alg[dom],
+                                "algorithmic_bytes": alg[dom], "issue": issue,
                                 "note": "blend kernels are fp32-issue/L2-reduction bound (~160 FLOP "
                                         "per algorithmic byte); see DESIGN.md and profiles/"}
             line["stage_ms"] = stages

@@ -243,6 +243,14 @@ constexpr int kBwdV2SmemBytes = kBlendStages * kBlendBatch * (int)sizeof(GcrReco
 
 struct BwdRec { float x, y, A, B, C, o; uint32_t gidx; };
 
+//
+// kApprox (experimental, env GCR_BWD_MATH=approx; not yet measured on hardware): the gradients
+// only have to meet the 1e-4 bar, so exp becomes ex2.approx(power * log2 e) (2 instructions instead
+// of ~10) and 1/(1-alpha) one MUFU.RCP (instead of the IEEE reciprocal's ~8).  The set of
+// contributors must still be EXACTLY the forward's (a flipped alpha >= 1/255 decision would
+// rescale the rest of that pixel's T chain), so any alpha within 1e-7 of the threshold -- 30x the
+// worst-case error of the approximation there -- is re-evaluated with the exact expf.
+template <bool kApprox>
 __global__ void __launch_bounds__(kBlendThreads)
 blend_bwd_kernel_v2(GcrBlendArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -414,14 +422,24 @@ blend_bwd_kernel_v2(GcrBlendArgs a) {
           const float dx = __fsub_rn(r0.x, pxf);
           const float dy = __fsub_rn(r0.y, pyf);
           const float power = gcr_power(dx, dy, r0.z, r0.w, r1.x);
-          const float G = expf(power);
-          const float alpha = fminf(0.99f, __fmul_rn(r1.y, G));
+          float G, alpha;
+          if (kApprox) {
+            G = gcr_ex2_approx(power * 1.4426950408889634f);
+            alpha = fminf(0.99f, r1.y * G);
+            if (fabsf(alpha - 1.0f / 255.0f) < 1e-7f) {   // borderline: decide exactly like the forward
+              G = expf(power);
+              alpha = fminf(0.99f, __fmul_rn(r1.y, G));
+            }
+          } else {
+            G = expf(power);
+            alpha = fminf(0.99f, __fmul_rn(r1.y, G));
+          }
           // reference: contributor-- ; if (contributor >= last_contributor) continue; power > 0 and
           // alpha < 1/255 skip as well
           const bool contrib = (lo + jj < last_contributor) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
           float wA = 0.f, wB = 0.f, wG = 0.f;
           if (contrib) {
-            const float inv_1ma = __frcp_rn(1.f - alpha);
+            const float inv_1ma = kApprox ? gcr_rcp_approx(1.f - alpha) : __frcp_rn(1.f - alpha);
             T = T * inv_1ma;
             const float one_m_la = 1.f - last_alpha;
             acc0 = fmaf(last_alpha, lc0, one_m_la * acc0);
@@ -468,13 +486,22 @@ void gcr_launch_blend_bwd(const GcrBlendArgs& a, cudaStream_t stream) {
     blend_bwd_kernel<<<grid, kBlendThreads, 0, stream>>>(a);
     return;
   }
+  static const bool approx = [] {
+    const char* e = getenv("GCR_BWD_MATH");
+    return e != nullptr && e[0] == 'a';
+  }();
   static bool configured[64] = {};   // the opt-in shared-memory size is a per-device attribute
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !configured[dev]) {
-    cudaFuncSetAttribute(blend_bwd_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(blend_bwd_kernel_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         kBwdV2SmemBytes);
+    cudaFuncSetAttribute(blend_bwd_kernel_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          kBwdV2SmemBytes);
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
-  blend_bwd_kernel_v2<<<grid, kBlendThreads, kBwdV2SmemBytes, stream>>>(a);
+  if (approx)
+    blend_bwd_kernel_v2<true><<<grid, kBlendThreads, kBwdV2SmemBytes, stream>>>(a);
+  else
+    blend_bwd_kernel_v2<false><<<grid, kBlendThreads, kBwdV2SmemBytes, stream>>>(a);
 }

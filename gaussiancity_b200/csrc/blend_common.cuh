@@ -43,3 +43,16 @@ __forceinline__ __device__ bool gcr_subrect_touch(float mx, float my, float A, f
   const bool cull = pd && (qmin > twoL + 1e-5f * mag + 1e-3f);
   return !cull;
 }
+
+// Approximate SFU forms for paths that only carry a tolerance (never the forward):
+// ex2.approx.ftz (<= 2 ulp) and rcp.approx.ftz (<= 1 ulp), one MUFU each.
+__forceinline__ __device__ float gcr_ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__forceinline__ __device__ float gcr_rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
