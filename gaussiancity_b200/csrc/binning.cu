@@ -334,22 +334,13 @@ __device__ __forceinline__ uint32_t digit_excl_scan(uint32_t v, uint32_t* smem) 
 // kThreads x kItems pairs per tile (256 x 16 = 4096 by default; 256 x 4 = 1024 for small inputs,
 // where the 16 serial ranking rounds of a few lonely CTAs are the whole latency); all shared
 // memory dynamic.
-//
-// kEarlyStage (experimental, env GCR_SORT_ORDER=early; not yet measured on hardware): the ncu
-// source view of the default order (profiles/r01_ncu_source_hotspots.md) puts ~30 % of the
-// samples in the look-back spin -- predecessors that have not published yet -- and ~12 % on the
-// value loads that are only issued after it.  Staging needs the tile-local digit starts only, so
-// this order publishes the tile aggregate first, then loads + stages the values, and only then
-// walks back: the predecessors get that time to publish, and the value-load latency overlaps it.
-// `spin_ns` > 0 backs the spin off with __nanosleep (fewer issue slots / L2 polls while waiting).
-template <bool kIota, int kThreads, int kItems, bool kEarlyStage>
+template <bool kIota, int kThreads, int kItems>
 __global__ void __launch_bounds__(kThreads, kThreads == 256 ? 4 : 2)
 onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                      uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, size_t n,
                      int shift, uint32_t digit_mask, int nbits,
                      const uint32_t* __restrict__ ghist_pass /* [kBins] */,
-                     volatile uint32_t* status /* [tiles][kBins], zeroed */, uint32_t* ticket,
-                     unsigned spin_ns) {
+                     volatile uint32_t* status /* [tiles][kBins], zeroed */, uint32_t* ticket) {
   constexpr int kWarps = kThreads / 32;
   constexpr int kTile = kThreads * kItems;
   extern __shared__ __align__(16) uint32_t os_smem[];
@@ -396,8 +387,46 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
   }
   __syncthreads();
 
-  // stage this tile's pairs into shared memory in digit order (needs bstart + the per-warp bases)
-  auto stage_pairs = [&]() {
+  {
+    uint32_t acc = 0;   // this tile's count of digit `tid` (threads >= kBins idle here)
+    if (tid < kBins) {
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) {
+        const uint32_t t = warp_hist[w][tid];
+        warp_hist[w][tid] = acc;
+        acc += t;
+      }
+    }
+    const uint32_t bs = digit_excl_scan(acc, sm);
+    const uint32_t dstart = digit_excl_scan(tid < kBins ? ghist_pass[tid] : 0u, sm);
+    if (tid < kBins) {
+      bstart[tid] = bs;
+      // decoupled look-back over the predecessors' status words for this digit
+      volatile uint32_t* mine = status + (size_t)tile * kBins + tid;
+      uint32_t excl = 0;
+      if (tile == 0) {
+        *mine = kFlagIncl | acc;
+      } else {
+        *mine = kFlagAgg | acc;
+        // (an 8-wide batched walk was measured: no faster -- the wait is for predecessors to
+        // publish, not for the L2 round trips of the walk itself)
+        long long t = (long long)tile - 1;
+        while (true) {
+          const uint32_t v = status[(size_t)t * kBins + tid];
+          const uint32_t f = v & ~kValMask;
+          if (f == 0u) continue;              // predecessor has not published yet: spin
+          excl += v & kValMask;
+          if (f == kFlagIncl) break;
+          --t;
+        }
+        *mine = kFlagIncl | (excl + acc);
+      }
+      gbase[tid] = dstart + excl;
+    }
+  }
+  __syncthreads();
+
+  {
     uint32_t val[kItems];
 #pragma unroll
     for (int r = 0; r < kItems; ++r) {
@@ -414,71 +443,6 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
         st_vals[pos] = val[r];
       }
     }
-  };
-  // decoupled look-back over the predecessors' status words for digit `tid` (tile > 0)
-  auto look_back = [&]() -> uint32_t {
-    uint32_t excl = 0;
-    // (an 8-wide batched walk was measured: no faster -- the wait is for predecessors to
-    // publish, not for the L2 round trips of the walk itself)
-    long long t = (long long)tile - 1;
-    while (true) {
-      const uint32_t v = status[(size_t)t * kBins + tid];
-      const uint32_t f = v & ~kValMask;
-      if (f == 0u) {                        // predecessor has not published yet: spin
-        if (spin_ns) __nanosleep(spin_ns);
-        continue;
-      }
-      excl += v & kValMask;
-      if (f == kFlagIncl) break;
-      --t;
-    }
-    return excl;
-  };
-
-  {
-    uint32_t acc = 0;   // this tile's count of digit `tid` (threads >= kBins idle here)
-    if (tid < kBins) {
-#pragma unroll
-      for (int w = 0; w < kWarps; ++w) {
-        const uint32_t t = warp_hist[w][tid];
-        warp_hist[w][tid] = acc;
-        acc += t;
-      }
-    }
-    const uint32_t bs = digit_excl_scan(acc, sm);
-    const uint32_t dstart = digit_excl_scan(tid < kBins ? ghist_pass[tid] : 0u, sm);
-    volatile uint32_t* mine = status + (size_t)tile * kBins + tid;
-    if (kEarlyStage) {
-      if (tid < kBins) {
-        bstart[tid] = bs;
-        *mine = (tile == 0 ? kFlagIncl : kFlagAgg) | acc;   // publish before staging
-      }
-      __syncthreads();                                      // bstart / warp bases visible
-      stage_pairs();
-      if (tid < kBins) {
-        uint32_t excl = 0;
-        if (tile != 0) {
-          excl = look_back();
-          *mine = kFlagIncl | (excl + acc);
-        }
-        gbase[tid] = dstart + excl;
-      }
-    } else {
-      if (tid < kBins) {
-        bstart[tid] = bs;
-        uint32_t excl = 0;
-        if (tile == 0) {
-          *mine = kFlagIncl | acc;
-        } else {
-          *mine = kFlagAgg | acc;
-          excl = look_back();
-          *mine = kFlagIncl | (excl + acc);
-        }
-        gbase[tid] = dstart + excl;
-      }
-      __syncthreads();
-      stage_pairs();
-    }
   }
   __syncthreads();
 
@@ -493,13 +457,15 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
 }
 
 // Early-counts order (experimental, env GCR_SORT_ORDER=counts; not yet measured on hardware).
-// In the default order a tile only publishes its digit counts after the 16 ballot-ranking rounds,
+// The ncu source view of the default order (profiles/r01_ncu_source_hotspots.md) puts ~30 % of the
+// samples in the look-back spin and ~12 % on the value loads issued behind it: a tile only publishes its digit counts after the 16 ballot-ranking rounds,
 // so ranking sits on the inter-tile dependency chain (the look-back of tile t waits for tile
 // t-1's ranking).  Here the counts come first -- one shared-memory atomic per key, no order
 // needed -- and the aggregate is published before any ranking; the ranking then starts from the
 // scanned per-warp bases and yields tile positions directly (keys go to the staging buffer inside
 // the ranking loop), the values follow, and the look-back runs last, when the predecessors have
 // long published.  Same outputs as onesweep_pass_kernel (stable within tile and across tiles).
+// `spin_ns` > 0 (env GCR_SORT_SPIN_NS) backs the remaining spin off with __nanosleep.
 template <bool kIota, int kThreads, int kItems>
 __global__ void __launch_bounds__(kThreads, kThreads == 256 ? 4 : 2)
 onesweep_pass_counts_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
@@ -630,12 +596,12 @@ onesweep_pass_counts_kernel(const uint32_t* __restrict__ keys_in, const uint32_t
   }
 }
 
-struct SortTuning { int order; unsigned spin_ns; };   // order: 0 default, 1 early staging, 2 early counts
+struct SortTuning { bool counts; unsigned spin_ns; };
 static SortTuning sort_tuning() {
   static const SortTuning t = [] {
-    SortTuning r{0, 0u};
+    SortTuning r{false, 0u};
     const char* o = getenv("GCR_SORT_ORDER");
-    if (o != nullptr) r.order = o[0] == 'e' ? 1 : (o[0] == 'c' ? 2 : 0);
+    r.counts = o != nullptr && o[0] == 'c';
     const char* s = getenv("GCR_SORT_SPIN_NS");
     if (s != nullptr) r.spin_ns = (unsigned)max(0, atoi(s));
     return r;
@@ -643,42 +609,25 @@ static SortTuning sort_tuning() {
   return t;
 }
 
-template <bool kIota, int kThreads, int kItems, bool kEarlyStage>
-void launch_onesweep_variant(unsigned tiles, cudaStream_t stream, const uint32_t* kin, const uint32_t* vin,
-                             uint32_t* kout, uint32_t* vout, size_t n, int shift, uint32_t mask, int bits,
-                             const uint32_t* ghist, uint32_t* st, uint32_t* ticket, unsigned spin_ns) {
+template <bool kIota, int kThreads, int kItems>
+void launch_onesweep_pass(unsigned tiles, cudaStream_t stream, const uint32_t* kin, const uint32_t* vin,
+                          uint32_t* kout, uint32_t* vout, size_t n, int shift, uint32_t mask, int bits,
+                          const uint32_t* ghist, uint32_t* st, uint32_t* ticket) {
   constexpr int smem = ((kThreads / 32) * kBins + 2 * kBins + 16 + 2 * kThreads * kItems) * 4;
   static bool configured[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !configured[dev]) {
-    cudaFuncSetAttribute(onesweep_pass_kernel<kIota, kThreads, kItems, kEarlyStage>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(onesweep_pass_kernel<kIota, kThreads, kItems>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(onesweep_pass_counts_kernel<kIota, kThreads, kItems>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
-  onesweep_pass_kernel<kIota, kThreads, kItems, kEarlyStage><<<tiles, kThreads, smem, stream>>>(
-      kin, vin, kout, vout, n, shift, mask, bits, ghist, st, ticket, spin_ns);
-}
-
-template <bool kIota, int kThreads, int kItems>
-void launch_onesweep_pass(unsigned tiles, cudaStream_t stream, const uint32_t* kin, const uint32_t* vin,
-                          uint32_t* kout, uint32_t* vout, size_t n, int shift, uint32_t mask, int bits,
-                          const uint32_t* ghist, uint32_t* st, uint32_t* ticket) {
   const SortTuning t = sort_tuning();
-  if (t.order == 2) {
-    constexpr int smem = ((kThreads / 32) * kBins + 2 * kBins + 16 + 2 * kThreads * kItems) * 4;
-    static bool configured[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || !configured[dev]) {
-      cudaFuncSetAttribute(onesweep_pass_counts_kernel<kIota, kThreads, kItems>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      if (dev >= 0 && dev < 64) configured[dev] = true;
-    }
+  if (t.counts)
     onesweep_pass_counts_kernel<kIota, kThreads, kItems><<<tiles, kThreads, smem, stream>>>(
         kin, vin, kout, vout, n, shift, mask, bits, ghist, st, ticket, t.spin_ns);
-  } else if (t.order == 1)
-    launch_onesweep_variant<kIota, kThreads, kItems, true>(tiles, stream, kin, vin, kout, vout, n, shift, mask, bits, ghist, st, ticket, t.spin_ns);
   else
-    launch_onesweep_variant<kIota, kThreads, kItems, false>(tiles, stream, kin, vin, kout, vout, n, shift, mask, bits, ghist, st, ticket, t.spin_ns);
+    onesweep_pass_kernel<kIota, kThreads, kItems><<<tiles, kThreads, smem, stream>>>(kin, vin, kout, vout, n, shift, mask, bits, ghist, st, ticket);
 }
 
 // ------------------------------------------------------------------------------------------

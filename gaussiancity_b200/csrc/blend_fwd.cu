@@ -17,11 +17,18 @@
 // eight have (block vote once per batch).  Arithmetic per pixel is pinned to the reference's
 // SASS order (gcr_power, expf, fma order of the colour accumulation), so final_T / n_contrib
 // are bit-identical.
+#include <cstdlib>
 #include "blend_common.cuh"
 #include "gcr_kernels.h"
 
 namespace {
 
+// kTrim (experimental, env GCR_BLEND_FWD=trim; not yet run on hardware): the ncu source view
+// counts 52 SASS instructions per surviving (warp, record); this variant folds the loop-invariant
+// parts of the record address and of the list position out of the survivor loop; nvcc then also
+// if-converts the state update (no inner branch): 49 instructions, identical arithmetic.  (Holding
+// libdevice's expf constants in registers was tried too: ptxas re-materialises them regardless.)
+template <bool kTrim>
 __global__ void __launch_bounds__(kBlendThreads)
 blend_fwd_kernel(GcrBlendArgs a) {
   __shared__ __align__(128) GcrRecord stage[kBlendStages][kBlendBatch];
@@ -90,28 +97,56 @@ blend_fwd_kernel(GcrBlendArgs a) {
           touch = gcr_subrect_touch(q0.x, q0.y, q0.z, q0.w, q1.x, twoL, rx0, rx1, ry0, ry1);
         }
         unsigned mask = __ballot_sync(0xffffffffu, touch);
-        while (mask) {
-          const int jj = g0 + __ffs(mask) - 1;
-          mask &= mask - 1;
-          const float4 r0 = st[jj].q0;   // x, y, A, B   (broadcast LDS.128)
-          const float4 r1 = st[jj].q1;   // C, o, r, g
-          // straight-line evaluation, state updates predicated: same arithmetic as the reference
-          // on every contributing lane, no per-test branches (the warp is issue-bound)
-          const float dx = __fsub_rn(r0.x, pxf);
-          const float dy = __fsub_rn(r0.y, pyf);
-          const float power = gcr_power(dx, dy, r0.z, r0.w, r1.x);
-          const float alpha = fminf(0.99f, __fmul_rn(r1.y, expf(power)));
-          const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
-          const bool ok = !done && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
-          const bool sat = ok && (test_T < 0.0001f);
-          done = done || sat;
-          if (ok && !sat) {
-            const float cb = st[jj].q2.x;  // b
-            C0 = __fmaf_rn(T, __fmul_rn(alpha, r1.z), C0);
-            C1 = __fmaf_rn(T, __fmul_rn(alpha, r1.w), C1);
-            C2 = __fmaf_rn(T, __fmul_rn(alpha, cb), C2);
-            T = test_T;
-            last_contributor = (uint32_t)(b * kBlendBatch + jj + 1);
+        if (kTrim) {
+          const GcrRecord* __restrict__ stc = st + g0;        // chunk-invariant parts hoisted
+          const uint32_t pos1 = (uint32_t)(b * kBlendBatch + g0 + 1);
+          while (mask) {
+            const int bit = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const GcrRecord* __restrict__ rec = stc + bit;
+            const float4 r0 = rec->q0;   // x, y, A, B   (broadcast LDS.128)
+            const float4 r1 = rec->q1;   // C, o, r, g
+            const float dx = __fsub_rn(r0.x, pxf);
+            const float dy = __fsub_rn(r0.y, pyf);
+            const float power = gcr_power(dx, dy, r0.z, r0.w, r1.x);
+            const float alpha = fminf(0.99f, __fmul_rn(r1.y, expf(power)));
+            const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+            const bool ok = !done && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+            const bool sat = ok && (test_T < 0.0001f);
+            done = done || sat;
+            if (ok && !sat) {
+              const float cb = rec->q2.x;  // b
+              C0 = __fmaf_rn(T, __fmul_rn(alpha, r1.z), C0);
+              C1 = __fmaf_rn(T, __fmul_rn(alpha, r1.w), C1);
+              C2 = __fmaf_rn(T, __fmul_rn(alpha, cb), C2);
+              T = test_T;
+              last_contributor = pos1 + (uint32_t)bit;
+            }
+          }
+        } else {
+          while (mask) {
+            const int jj = g0 + __ffs(mask) - 1;
+            mask &= mask - 1;
+            const float4 r0 = st[jj].q0;   // x, y, A, B   (broadcast LDS.128)
+            const float4 r1 = st[jj].q1;   // C, o, r, g
+            // straight-line evaluation, state updates predicated: same arithmetic as the reference
+            // on every contributing lane, no per-test branches (the warp is issue-bound)
+            const float dx = __fsub_rn(r0.x, pxf);
+            const float dy = __fsub_rn(r0.y, pyf);
+            const float power = gcr_power(dx, dy, r0.z, r0.w, r1.x);
+            const float alpha = fminf(0.99f, __fmul_rn(r1.y, expf(power)));
+            const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+            const bool ok = !done && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+            const bool sat = ok && (test_T < 0.0001f);
+            done = done || sat;
+            if (ok && !sat) {
+              const float cb = st[jj].q2.x;  // b
+              C0 = __fmaf_rn(T, __fmul_rn(alpha, r1.z), C0);
+              C1 = __fmaf_rn(T, __fmul_rn(alpha, r1.w), C1);
+              C2 = __fmaf_rn(T, __fmul_rn(alpha, cb), C2);
+              T = test_T;
+              last_contributor = (uint32_t)(b * kBlendBatch + jj + 1);
+            }
           }
         }
         if (__ballot_sync(0xffffffffu, !done) == 0u) break;  // warp saturated
@@ -144,5 +179,13 @@ void gcr_launch_blend_fwd(const GcrBlendArgs& a, cudaStream_t stream) {
   const int rows = (a.grid_y - a.shard_rank + a.shard_count - 1) / a.shard_count;
   if (rows <= 0 || a.grid_x <= 0) return;
   dim3 grid(a.grid_x, rows, 1);
-  blend_fwd_kernel<<<grid, kBlendThreads, 0, stream>>>(a);
+  static const bool trim = [] {
+    const char* e = getenv("GCR_BLEND_FWD");
+    return e != nullptr && e[0] == 't';
+  }();
+  if (trim) {
+    blend_fwd_kernel<true><<<grid, kBlendThreads, 0, stream>>>(a);
+  } else {
+    blend_fwd_kernel<false><<<grid, kBlendThreads, 0, stream>>>(a);
+  }
 }
