@@ -18,6 +18,7 @@ import numpy as np
 import torch
 
 from . import ext as dgr_ext
+from .camera import PoseSettingsCache, w2c_host
 
 __all__ = [
     "RasterizeGaussiansFunction",
@@ -132,29 +133,18 @@ class GaussianRasterizer(torch.nn.Module):
                                                 self.raster_settings)
 
 
-def _quat_xyzw_to_matrix(q):
-    """Rotation matrix of a (qx,qy,qz,qw) quaternion in float64.  Uses scipy when present (the
-    reference does, DGR/__init__.py:355) so view matrices round to identical float32 values."""
-    q = np.asarray(q, dtype=np.float64)
-    try:
-        import scipy.spatial.transform
-        return scipy.spatial.transform.Rotation.from_quat(q).as_matrix()
-    except ImportError:  # same formula, normalised quaternion
-        x, y, z, w = q / np.linalg.norm(q)
-        return np.array([
-            [1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
-            [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
-            [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
-
-
 class GaussianRasterizerWrapper(torch.nn.Module):
     """GaussianCity's camera adapter (DGR/__init__.py:276-426): intrinsics K + sensor size give
     the FoV and an OpenGL-style projection with P[3,2] = -1; a pose (position, xyzw quaternion)
     gives w2c with the axis permutation [F|R|U] -> [R|U|F]; points are [N,14] =
-    xyz | opacity | scale | rotation | rgb; the image is flipped along W by default."""
+    xyz | opacity | scale | rotation | rgb; the image is flipped along W by default.
+
+    `fast_camera=True` (not in the reference) builds the per-pose settings on the host and uploads
+    them in one packed copy with an LRU pose cache (gaussiancity_b200/camera.py)
+    instead of the reference's device matmul + device 4x4 inverse + three small copies per call."""
 
     def __init__(self, K, sensor_size, flip_lr=True, flip_ud=False, z_near=0.01, z_far=50000.0,
-                 device=torch.device("cuda")):
+                 device=torch.device("cuda"), fast_camera=False):
         super().__init__()
         self.flip_lr, self.flip_ud = flip_lr, flip_ud
         self.z_near, self.z_far = z_near, z_far
@@ -163,6 +153,8 @@ class GaussianRasterizerWrapper(torch.nn.Module):
         self.sensor_size = sensor_size
         self.fov_x, self.fov_y = self._intrinsic_to_fov()
         self.P = self._get_projection_matrix()
+        self._pose_cache = (PoseSettingsCache(self._projection_host(), device) if fast_camera
+                            else None)
 
     def get_gaussian_rasterizer(self, cam_position, cam_quaternion):
         return GaussianRasterizer(
@@ -181,6 +173,9 @@ class GaussianRasterizerWrapper(torch.nn.Module):
                 2 * np.arctan2(self.sensor_size[1], 2 * fy))
 
     def _get_projection_matrix(self):
+        return torch.from_numpy(self._projection_host()).to(self.device)
+
+    def _projection_host(self):
         fx, fy, cx, cy = self.K[0, 0], self.K[1, 1], self.K[0, 2], self.K[1, 2]
         w, h = self.sensor_size[0], self.sensor_size[1]
         zn, zf = self.z_near, self.z_far
@@ -192,21 +187,19 @@ class GaussianRasterizerWrapper(torch.nn.Module):
         P[2, 2] = -(zf + zn) / (zf - zn)
         P[3, 2] = -1.0
         P[2, 3] = -2.0 * zf * zn / (zf - zn)
-        return torch.from_numpy(P).to(self.device)
+        return P
 
     def _get_w2c_matrix(self, cam_position, cam_quaternion):
-        if isinstance(cam_position, torch.Tensor):
-            cam_position = cam_position.cpu().numpy()
-        if isinstance(cam_quaternion, torch.Tensor):
-            cam_quaternion = cam_quaternion.cpu().numpy()
-        R = _quat_xyzw_to_matrix(cam_quaternion)[:, [1, 2, 0]]  # [F|R|U] -> [R|U|F]
-        Rt = np.zeros((4, 4), dtype=np.float32)
-        Rt[:3, :3] = R.transpose()
-        Rt[:3, [3]] = -R.transpose() @ cam_position[:, None]
-        Rt[3, 3] = 1.0
-        return torch.from_numpy(Rt).to(self.device)
+        return torch.from_numpy(w2c_host(cam_position, cam_quaternion)).to(self.device)
 
     def _get_gaussian_rasterization_settings(self, cam_position, cam_quaternion):
+        if self._pose_cache is not None:
+            view, proj, campos, bg = self._pose_cache.get(cam_position, cam_quaternion)
+            return GaussianRasterizationSettings(
+                img_h=self.sensor_size[1], img_w=self.sensor_size[0],
+                tanfovx=math.tan(self.fov_x * 0.5), tanfovy=math.tan(self.fov_y * 0.5), bg=bg,
+                scale_modifier=1.0, view_matrix=view, proj_matrix=proj, sh_degree=0, campos=campos,
+                prefiltered=False, debug=False)
         bg = torch.tensor([0.0, 0.0, 0.0], dtype=torch.float32, device=self.device)
         w2c = self._get_w2c_matrix(cam_position, cam_quaternion).transpose(0, 1)
         return GaussianRasterizationSettings(

@@ -110,3 +110,93 @@ def test_bench_kernel_count_formula():
     assert bench.tile_sort_passes(1920, 1080) == 2
     assert bench.kernels_per_step(1920, 1080) == 17
     assert bench.tile_sort_passes(128, 128) == 1
+
+
+# ---- GaussianRasterizerWrapper camera path against the reference's own settings ----
+
+def _wrapper_golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "camera", "wrapper_settings.npz"))
+
+
+def _golden_pose(gold, i):
+    pos, quat = gold["cam_pos"][i], gold["cam_quat"][i]
+    if gold["pose_is_f32"][i]:
+        pos, quat = pos.astype(np.float32), quat.astype(np.float32)
+    return pos, quat
+
+
+@pytest.mark.parametrize("fast", [False, True], ids=["reference_sequence", "fast_camera"])
+def test_wrapper_settings_match_reference_golden(fast):
+    """tests/golden/camera/wrapper_settings.npz holds what the UNMODIFIED reference wrapper hands to the
+    rasterizer for an orbit of poses (generated by tests/golden/camera/make_wrapper_golden.py)."""
+    gold = _wrapper_golden()
+    w = g.GaussianRasterizerWrapper(gold["K"], tuple(int(v) for v in gold["sensor"]),
+                                    device=torch.device("cpu"), fast_camera=fast)
+    assert np.array_equal(w.P.numpy(), gold["P"])
+    for i in range(gold["cam_pos"].shape[0]):
+        pos, quat = _golden_pose(gold, i)
+        st = w._get_gaussian_rasterization_settings(pos, quat)
+        assert (st.tanfovx, st.tanfovy) == (gold["tanfov"][0], gold["tanfov"][1])
+        # host expression is the reference's own: bit-identical view matrix on both paths
+        assert np.array_equal(st.view_matrix.numpy(), gold["view"][i])
+        # proj: a 4-term fp32 dot product per element -- within 1 ulp of the row's magnitude
+        tol = 2.0 ** -22 * np.abs(gold["proj"][i]).max(axis=1, keepdims=True)
+        assert (np.abs(st.proj_matrix.numpy().astype(np.float64) - gold["proj"][i]) <= tol).all()
+        # campos: the reference inverts the fp32 view matrix; the true centre is cam_pos
+        assert np.allclose(st.campos.numpy(), gold["campos"][i], atol=2e-3)
+        assert np.allclose(st.campos.numpy(), gold["cam_pos"][i], atol=2e-3)
+        assert st.bg.shape == (3,) and float(st.bg.abs().sum()) == 0.0
+        for t in (st.view_matrix, st.proj_matrix, st.campos, st.bg):
+            assert t.dtype == torch.float32
+            assert t.is_contiguous() or not fast   # (the reference hands over a transposed view)
+        if fast:
+            assert np.array_equal(st.campos.numpy(), pos.astype(np.float32))
+
+
+def test_fast_camera_cache_uploads_once_per_pose():
+    gold = _wrapper_golden()
+    w = g.GaussianRasterizerWrapper(gold["K"], (960, 540), device=torch.device("cpu"), fast_camera=True)
+    c = w._pose_cache
+    poses = [_golden_pose(gold, i) for i in range(4)]
+    first = [w._get_gaussian_rasterization_settings(*p) for p in poses]
+    assert c.uploads == 4
+    again = [w._get_gaussian_rasterization_settings(*p) for p in poses]
+    assert c.uploads == 4                                     # all hits
+    for a, b in zip(first, again):
+        assert a.view_matrix.data_ptr() == b.view_matrix.data_ptr()
+    # torch tensors as pose, same values -> same entry as the numpy pose
+    w._get_gaussian_rasterization_settings(torch.from_numpy(poses[0][0]), torch.from_numpy(poses[0][1]))
+    assert c.uploads == 4
+    # a different dtype of the same pose is a different key (the reference computes in that dtype)
+    w._get_gaussian_rasterization_settings(poses[0][0].astype(np.float32), poses[0][1])
+    assert c.uploads == 5
+    # LRU eviction
+    c.capacity = 2
+    for i in range(4, 8):
+        w._get_gaussian_rasterization_settings(*_golden_pose(gold, i))
+    assert len(c._lru) == 2
+    # 16-byte alignment of every section of the packed upload
+    st = w._get_gaussian_rasterization_settings(*poses[1])
+    base = st.view_matrix.data_ptr()
+    assert (st.proj_matrix.data_ptr() - base, st.campos.data_ptr() - base, st.bg.data_ptr() - base) == (64, 128, 144)
+
+
+def test_fast_camera_renders_the_same_image_as_the_reference_sequence():
+    """End to end through the CPU oracle (no GPU here): the settings of both camera paths give the
+    same frame within the colour bar (<= 1e-4; the matrices differ by at most the last bit)."""
+    from gaussiancity_b200.synthetic import city_points
+    from oracle import oracle
+    pts, cam_pos, cam_quat = city_points(600, seed=3)
+    imgs = []
+    for fast in (False, True):
+        w = g.GaussianRasterizerWrapper(CITY_K, CITY_SENSOR, device=torch.device("cpu"), fast_camera=fast)
+        st = w._get_gaussian_rasterization_settings(cam_pos, cam_quat)
+        p = pts.numpy()
+        r = oracle.forward(p[:, 0:3], p[:, 3:4], p[:, 4:7], p[:, 7:11], st.view_matrix.contiguous().numpy(),
+                           st.proj_matrix.contiguous().numpy(), st.campos.numpy(), st.img_w, st.img_h,
+                           st.tanfovx, st.tanfovy, st.bg.numpy(), colors_precomp=p[:, 11:14])
+        assert r.num_rendered > 0
+        imgs.append(np.asarray(r.color, np.float64))
+    den = np.linalg.norm(imgs[0])
+    assert den > 0 and np.linalg.norm(imgs[0] - imgs[1]) / den <= 1e-4
