@@ -37,13 +37,13 @@ def _sh_to_rgb(deg, shs, dirs):
     return torch.clamp_min(res + 0.5, 0.0)
 
 
-def render_naive(s):
-    """s: gaussiancity_b200.synthetic.Scene with CPU tensors -> (color[3,H,W], radii[P])."""
-    f32 = torch.float32
+def _preprocess(s, dt):
+    """Per-Gaussian forward quantities (DGR forward.cu:147-233), vectorised over Gaussians, in dtype
+    `dt`; differentiable w.r.t. any input tensor of `s` that requires grad."""
     P, W, H = s.means3D.shape[0], s.img_w, s.img_h
-    V, PM = s.view_matrix.to(f32), s.proj_matrix.to(f32)     # transposed (row-vector) matrices
-    p = s.means3D.to(f32)
-    ph = torch.cat([p, torch.ones(P, 1)], dim=1)
+    V, PM = s.view_matrix.to(dt), s.proj_matrix.to(dt)        # transposed (row-vector) matrices
+    p = s.means3D.to(dt)
+    ph = torch.cat([p, torch.ones(P, 1, dtype=dt)], dim=1)
     view = ph @ V                                             # [P,4] camera space
     hom = ph @ PM
     pw = 1.0 / (hom[:, 3] + 1e-7)
@@ -51,22 +51,22 @@ def render_naive(s):
     tz = view[:, 2]
     visible = tz > 0.2
     # 3D covariance  Sigma = R S^2 R^T with the UN-normalised quaternion (r, x, y, z)
-    q = s.rotations.to(f32)
+    q = s.rotations.to(dt)
     r, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
     R = torch.stack([
         torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y)], dim=1),
         torch.stack([2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x)], dim=1),
         torch.stack([2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)], dim=1)], dim=1)
-    Sg = R @ torch.diag_embed(s.scales.to(f32) ** 2) @ R.transpose(1, 2)
+    Sg = R @ torch.diag_embed(s.scales.to(dt) ** 2) @ R.transpose(1, 2)
     # EWA projection
     fx, fy = W / (2.0 * s.tanfovx), H / (2.0 * s.tanfovy)
     limx, limy = 1.3 * s.tanfovx, 1.3 * s.tanfovy
     tzs = torch.where(visible, tz, torch.ones_like(tz))
     tx = torch.clamp(view[:, 0] / tzs, -limx, limx) * tzs
     ty = torch.clamp(view[:, 1] / tzs, -limy, limy) * tzs
-    J = torch.zeros(P, 2, 3)
-    J[:, 0, 0], J[:, 0, 2] = fx / tzs, -fx * tx / (tzs * tzs)
-    J[:, 1, 1], J[:, 1, 2] = fy / tzs, -fy * ty / (tzs * tzs)
+    zero = torch.zeros_like(tzs)
+    J = torch.stack([torch.stack([fx / tzs, zero, -fx * tx / (tzs * tzs)], dim=1),
+                     torch.stack([zero, fy / tzs, -fy * ty / (tzs * tzs)], dim=1)], dim=1)   # [P,2,3]
     Rw = V[:3, :3].T                                          # world -> camera rotation
     T = J @ Rw
     cov = T @ Sg @ T.transpose(1, 2)
@@ -77,31 +77,44 @@ def render_naive(s):
     conic = torch.stack([c / dets, -b / dets, a / dets], dim=1)
     mid = 0.5 * (a + c)
     lam = mid + torch.sqrt(torch.clamp_min(mid * mid - det, 0.1))
-    radius = torch.ceil(3.0 * torch.sqrt(torch.where(ok, lam, torch.ones_like(lam))))
+    radius = torch.ceil(3.0 * torch.sqrt(torch.where(ok, lam, torch.ones_like(lam)))).detach()
     px = ((ndc[:, 0].double() + 1.0) * W - 1.0) * 0.5
     py = ((ndc[:, 1].double() + 1.0) * H - 1.0) * 0.5
-    px, py = px.to(f32), py.to(f32)
+    px, py = px.to(dt), py.to(dt)
     gx, gy = (W + 15) // 16, (H + 15) // 16
-    x0 = torch.clamp(torch.trunc((px - radius) / 16), 0, gx)
-    y0 = torch.clamp(torch.trunc((py - radius) / 16), 0, gy)
-    x1 = torch.clamp(torch.trunc((px + radius + 15) / 16), 0, gx)
-    y1 = torch.clamp(torch.trunc((py + radius + 15) / 16), 0, gy)
+    pxd, pyd = px.detach(), py.detach()
+    x0 = torch.clamp(torch.trunc((pxd - radius) / 16), 0, gx)
+    y0 = torch.clamp(torch.trunc((pyd - radius) / 16), 0, gy)
+    x1 = torch.clamp(torch.trunc((pxd + radius + 15) / 16), 0, gx)
+    y1 = torch.clamp(torch.trunc((pyd + radius + 15) / 16), 0, gy)
     ok = ok & ((x1 - x0) * (y1 - y0) > 0)
     radii = torch.where(ok, radius, torch.zeros_like(radius)).to(torch.int32)
     if s.colors_precomp is not None:
-        rgb = s.colors_precomp.to(f32)
+        rgb = s.colors_precomp.to(dt)
     else:
-        d = p - s.campos.to(f32)[None]
-        rgb = _sh_to_rgb(s.sh_degree, s.shs.to(f32), d / d.norm(dim=1, keepdim=True))
-    opac = s.opacities.to(f32).reshape(-1)
-    # front-to-back over Gaussians in (depth, index) order, all pixels at once
+        d = p - s.campos.to(dt)[None]
+        rgb = _sh_to_rgb(s.sh_degree, s.shs.to(dt), d / d.norm(dim=1, keepdim=True))
+    opac = s.opacities.to(dt).reshape(-1)
     idx = torch.nonzero(ok).flatten()
-    order = idx[torch.sort(tz[idx], stable=True).indices]
+    order = idx[torch.sort(tz.detach()[idx], stable=True).indices]
+    return dict(ndc=ndc, px=px, py=py, conic=conic, rgb=rgb, opac=opac, radii=radii, order=order,
+                rect=(x0, x1, y0, y1))
+
+
+def render_naive(s):
+    """s: gaussiancity_b200.synthetic.Scene with CPU tensors -> (color[3,H,W], radii[P]); fp32."""
+    f32 = torch.float32
+    W, H = s.img_w, s.img_h
+    with torch.no_grad():
+        q = _preprocess(s, f32)
+    px, py, conic, rgb, opac = q["px"], q["py"], q["conic"], q["rgb"], q["opac"]
+    x0, x1, y0, y1 = q["rect"]
+    # front-to-back over Gaussians in (depth, index) order, all pixels of the splat's rectangle at once
     ys, xs = torch.meshgrid(torch.arange(H, dtype=f32), torch.arange(W, dtype=f32), indexing="ij")
     Tr = torch.ones(H, W)
     done = torch.zeros(H, W, dtype=torch.bool)
     C = torch.zeros(3, H, W)
-    for g in order.tolist():
+    for g in q["order"].tolist():
         rx0, rx1, ry0, ry1 = int(x0[g]) * 16, int(x1[g]) * 16, int(y0[g]) * 16, int(y1[g]) * 16
         sl = (slice(ry0, min(ry1, H)), slice(rx0, min(rx1, W)))       # the reference's tile rectangle
         dx, dy = px[g] - xs[sl], py[g] - ys[sl]
@@ -115,4 +128,37 @@ def render_naive(s):
         w = torch.where(upd, alpha * Tr[sl], torch.zeros_like(alpha))
         C[:, sl[0], sl[1]] += rgb[g][:, None, None] * w[None]
         Tr[sl] = torch.where(upd, test_T, Tr[sl])
-    return C + Tr[None] * s.bg.to(f32)[:, None, None], radii
+    return C + Tr[None] * s.bg.to(f32)[:, None, None], q["radii"]
+
+
+def render_autograd(s, dtype=torch.float64):
+    """Differentiable restatement for gradient ground truth (SURVEY 8c "fp64 + autograd"): the same
+    forward written functionally (no in-place updates), so torch.autograd differentiates it.  The
+    thresholds (alpha < 1/255, T < 1e-4, the 0.99 cap, the frustum clamp of t, the SH clamp at 0)
+    are piecewise constant exactly as the reference's analytic backward treats them
+    (DGR backward.cu).  Returns (color[3,H,W], ndc[P,2]); `ndc` is the retained intermediate whose
+    gradient is the reference's `dL_dmeans2D` ("viewspace points").  Small scenes only: every
+    Gaussian touches a full-image tensor."""
+    W, H = s.img_w, s.img_h
+    q = _preprocess(s, dtype)
+    q["ndc"].retain_grad()
+    px, py, conic, rgb, opac = q["px"], q["py"], q["conic"], q["rgb"], q["opac"]
+    x0, x1, y0, y1 = q["rect"]
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=dtype), torch.arange(W, dtype=dtype), indexing="ij")
+    Tr = torch.ones(H, W, dtype=dtype)
+    done = torch.zeros(H, W, dtype=torch.bool)
+    C = torch.zeros(3, H, W, dtype=dtype)
+    for g in q["order"].tolist():
+        inrect = ((xs >= int(x0[g]) * 16) & (xs < int(x1[g]) * 16) &
+                  (ys >= int(y0[g]) * 16) & (ys < int(y1[g]) * 16))
+        dx, dy = px[g] - xs, py[g] - ys
+        power = -0.5 * (conic[g, 0] * dx * dx + conic[g, 2] * dy * dy) - conic[g, 1] * dx * dy
+        alpha = torch.clamp_max(opac[g] * torch.exp(torch.clamp_max(power, 0.0)), 0.99)
+        contrib = inrect & (~done) & (power.detach() <= 0) & (alpha.detach() >= 1.0 / 255.0)
+        test_T = Tr * (1 - alpha)
+        sat = contrib & (test_T.detach() < 1e-4)
+        done = done | sat
+        upd = contrib & ~sat
+        C = C + rgb[g][:, None, None] * torch.where(upd, alpha * Tr, torch.zeros_like(alpha))[None]
+        Tr = torch.where(upd, test_T, Tr)
+    return C + Tr[None] * s.bg.to(dtype)[:, None, None], q["ndc"]
