@@ -131,12 +131,16 @@ def render_naive(s):
     return C + Tr[None] * s.bg.to(f32)[:, None, None], q["radii"]
 
 
-def render_autograd(s, dtype=torch.float64):
+def render_autograd(s, dtype=torch.float64, reference_cap_gradient=True):
     """Differentiable restatement for gradient ground truth (SURVEY 8c "fp64 + autograd"): the same
     forward written functionally (no in-place updates), so torch.autograd differentiates it.  The
-    thresholds (alpha < 1/255, T < 1e-4, the 0.99 cap, the frustum clamp of t, the SH clamp at 0)
-    are piecewise constant exactly as the reference's analytic backward treats them
-    (DGR backward.cu).  Returns (color[3,H,W], ndc[P,2]); `ndc` is the retained intermediate whose
+    thresholds (alpha < 1/255, T < 1e-4, the frustum clamp of t, the SH clamp at 0) are piecewise
+    constant exactly as the reference's analytic backward treats them (DGR backward.cu).  One
+    reference quirk is reproduced on request (default): backward.cu:523,562,578 recomputes
+    `alpha = min(0.99, o G)` but propagates `dL/dalpha` to G and o as if the cap were not there, so
+    with `reference_cap_gradient=True` the cap is applied straight-through (capped value, identity
+    gradient); with False the mathematically exact derivative (zero where capped) is taken -- the two
+    differ wherever o G > 0.99, i.e. all over GaussianCity's opacity-1 scenes.  Returns (color[3,H,W], ndc[P,2]); `ndc` is the retained intermediate whose
     gradient is the reference's `dL_dmeans2D` ("viewspace points").  Small scenes only: every
     Gaussian touches a full-image tensor."""
     W, H = s.img_w, s.img_h
@@ -153,7 +157,10 @@ def render_autograd(s, dtype=torch.float64):
                   (ys >= int(y0[g]) * 16) & (ys < int(y1[g]) * 16))
         dx, dy = px[g] - xs, py[g] - ys
         power = -0.5 * (conic[g, 0] * dx * dx + conic[g, 2] * dy * dy) - conic[g, 1] * dx * dy
-        alpha = torch.clamp_max(opac[g] * torch.exp(torch.clamp_max(power, 0.0)), 0.99)
+        raw = opac[g] * torch.exp(torch.clamp_max(power, 0.0))
+        alpha = torch.clamp_max(raw, 0.99)
+        if reference_cap_gradient:
+            alpha = raw + (alpha - raw).detach()
         contrib = inrect & (~done) & (power.detach() <= 0) & (alpha.detach() >= 1.0 / 255.0)
         test_T = Tr * (1 - alpha)
         sat = contrib & (test_T.detach() < 1e-4)

@@ -155,6 +155,28 @@ def test_oracle_precomputed_covariance_and_scale_modifier_paths():
     assert np.all(g["dL_dscale"] == 0) and np.all(g["dL_drot"] == 0) and np.abs(g["dL_dcov3D"]).sum() > 0
 
 
+def _autograd_vs_oracle(s32, cn, seed, **kw):
+    from oracle import torch_naive
+    leaves = {n: getattr(s32, n).to(torch.float64).clone().requires_grad_(True)
+              for n in ("means3D", "opacities", "scales", "rotations", cn)}
+    col, ndc = torch_naive.render_autograd(s32._replace(**leaves), **kw)
+    G = torch.from_numpy(np.random.default_rng(seed).standard_normal((3, s32.img_h, s32.img_w)))
+    (col * G).sum().backward()
+    r = oracle.forward_scene(s32, "f64")
+    g = oracle.backward(r, G.numpy())
+    assert r.num_rendered > 0 and np.abs(col.detach().numpy() - r.color).max() < 1e-6
+    pairs = [("means3D", "dL_dmean3D"), ("opacities", "dL_dopacity"), ("scales", "dL_dscale"),
+             ("rotations", "dL_drot"), (cn, "dL_dsh" if cn == "shs" else "dL_dcolor")]
+    err = {}
+    for a, b in pairs:
+        x, y = leaves[a].grad.numpy().reshape(g[b].shape), g[b]
+        assert np.linalg.norm(y) > 0
+        err[a] = np.linalg.norm(x - y) / np.linalg.norm(y)
+    y = g["dL_dmean2D"]                                  # "viewspace points" gradient = d loss / d ndc
+    err["means2D"] = np.linalg.norm(ndc.grad.numpy() - y) / np.linalg.norm(y)
+    return err
+
+
 @pytest.mark.parametrize("P,W,H,deg,use_sh", [(200, 64, 48, 2, True), (150, 48, 32, 0, False), (120, 40, 40, 3, True)],
                          ids=["sh2", "precomp", "sh3"])
 def test_oracle_backward_matches_fp64_autograd(P, W, H, deg, use_sh):
@@ -163,22 +185,28 @@ def test_oracle_backward_matches_fp64_autograd(P, W, H, deg, use_sh):
     backward (the restated DGR backward.cu) on the same inputs.  They agree to ~5e-8 (the oracle
     keeps the reference's float literals); the bar here is 1e-6 per tensor."""
     from gaussiancity_b200.synthetic import uniform_scene
-    from oracle import torch_naive
     s32 = uniform_scene(P, W, H, sh_degree=deg, seed=deg + 11, use_sh=use_sh, bg=(0.1, 0.2, 0.3))
-    cn = "shs" if use_sh else "colors_precomp"
-    leaves = {n: getattr(s32, n).to(torch.float64).clone().requires_grad_(True)
-              for n in ("means3D", "opacities", "scales", "rotations", cn)}
-    col, ndc = torch_naive.render_autograd(s32._replace(**leaves))
-    G = torch.from_numpy(np.random.default_rng(deg).standard_normal((3, H, W)))
-    (col * G).sum().backward()
-    r = oracle.forward_scene(s32, "f64")
-    g = oracle.backward(r, G.numpy())
-    assert r.num_rendered > P and np.abs(col.detach().numpy() - r.color).max() < 1e-6
-    pairs = [("means3D", "dL_dmean3D"), ("opacities", "dL_dopacity"), ("scales", "dL_dscale"),
-             ("rotations", "dL_drot"), (cn, "dL_dsh" if use_sh else "dL_dcolor")]
-    for a, b in pairs:
-        x, y = leaves[a].grad.numpy().reshape(g[b].shape), g[b]
-        assert np.linalg.norm(y) > 0
-        assert np.linalg.norm(x - y) / np.linalg.norm(y) < 1e-6, (a, b)
-    y = g["dL_dmean2D"]                                  # "viewspace points" gradient = d loss / d ndc
-    assert np.linalg.norm(ndc.grad.numpy() - y) / np.linalg.norm(y) < 1e-6
+    err = _autograd_vs_oracle(s32, "shs" if use_sh else "colors_precomp", deg)
+    assert max(err.values()) < 1e-6, err
+
+
+def test_oracle_backward_matches_autograd_through_the_city_camera():
+    """Same check through GaussianCity's own call pattern: K / sensor camera with NEGATIVE clip-space
+    w (SURVEY 8a cheat-sheet: sign of mul1/mul2 in backward.cu:400-409), identity quaternions,
+    opacity 1.  Two reference quirks show up and are pinned here:
+      * the 0.99 alpha cap is differentiated straight-through by the reference (backward.cu:523,
+        562, 578) and therefore by the oracle and the CUDA path;
+        the exact derivative (zero where capped) differs by > 10 % on dL/dopacity in this scene;
+      * computeCov2D's backward uses 1/(denom^2 + 1e-7) (backward.cu:194), not the exact 1/denom^2:
+        a ~1e-5 relative effect on dL/dscale, dL/drot at this focal length."""
+    from gaussiancity_b200.synthetic import city_scene
+    s32 = city_scene(400, seed=2, scale=0.125, extent=64)
+    hom = torch.cat([s32.means3D, torch.ones(400, 1)], 1) @ s32.proj_matrix
+    assert (hom[:, 3] < 0).all()
+    err = _autograd_vs_oracle(s32, "colors_precomp", 0)
+    for k in ("means3D", "opacities", "colors_precomp", "means2D"):
+        assert err[k] < 1e-6, err
+    for k in ("scales", "rotations"):
+        assert err[k] < 5e-5, err
+    exact = _autograd_vs_oracle(s32, "colors_precomp", 0, reference_cap_gradient=False)
+    assert exact["opacities"] > 0.1 and exact["colors_precomp"] < 1e-6, exact
