@@ -37,7 +37,7 @@ def _sh_to_rgb(deg, shs, dirs):
     return torch.clamp_min(res + 0.5, 0.0)
 
 
-def _preprocess(s, dt):
+def _preprocess(s, dt, cov3D=None):
     """Per-Gaussian forward quantities (DGR forward.cu:147-233), vectorised over Gaussians, in dtype
     `dt`; differentiable w.r.t. any input tensor of `s` that requires grad."""
     P, W, H = s.means3D.shape[0], s.img_w, s.img_h
@@ -58,6 +58,11 @@ def _preprocess(s, dt):
         torch.stack([2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x)], dim=1),
         torch.stack([2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)], dim=1)], dim=1)
     Sg = R @ torch.diag_embed(s.scales.to(dt) ** 2) @ R.transpose(1, 2)
+    if cov3D is not None:     # precomputed covariance path: [P,6] = (S00,S01,S02,S11,S12,S22), forward.cu:138-143
+        c6 = cov3D.to(dt)
+        Sg = torch.stack([torch.stack([c6[:, 0], c6[:, 1], c6[:, 2]], dim=1),
+                          torch.stack([c6[:, 1], c6[:, 3], c6[:, 4]], dim=1),
+                          torch.stack([c6[:, 2], c6[:, 4], c6[:, 5]], dim=1)], dim=1)
     # EWA projection
     fx, fy = W / (2.0 * s.tanfovx), H / (2.0 * s.tanfovy)
     limx, limy = 1.3 * s.tanfovx, 1.3 * s.tanfovy
@@ -131,7 +136,7 @@ def render_naive(s):
     return C + Tr[None] * s.bg.to(f32)[:, None, None], q["radii"]
 
 
-def render_autograd(s, dtype=torch.float64, reference_cap_gradient=True):
+def render_autograd(s, dtype=torch.float64, reference_cap_gradient=True, cov3D=None):
     """Differentiable restatement for gradient ground truth (SURVEY 8c "fp64 + autograd"): the same
     forward written functionally (no in-place updates), so torch.autograd differentiates it.  The
     thresholds (alpha < 1/255, T < 1e-4, the frustum clamp of t, the SH clamp at 0) are piecewise
@@ -144,8 +149,9 @@ def render_autograd(s, dtype=torch.float64, reference_cap_gradient=True):
     gradient is the reference's `dL_dmeans2D` ("viewspace points").  Small scenes only: every
     Gaussian touches a full-image tensor."""
     W, H = s.img_w, s.img_h
-    q = _preprocess(s, dtype)
-    q["ndc"].retain_grad()
+    q = _preprocess(s, dtype, cov3D=cov3D)
+    if q["ndc"].requires_grad:
+        q["ndc"].retain_grad()
     px, py, conic, rgb, opac = q["px"], q["py"], q["conic"], q["rgb"], q["opac"]
     x0, x1, y0, y1 = q["rect"]
     ys, xs = torch.meshgrid(torch.arange(H, dtype=dtype), torch.arange(W, dtype=dtype), indexing="ij")

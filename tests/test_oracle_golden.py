@@ -210,3 +210,26 @@ def test_oracle_backward_matches_autograd_through_the_city_camera():
         assert err[k] < 5e-5, err
     exact = _autograd_vs_oracle(s32, "colors_precomp", 0, reference_cap_gradient=False)
     assert exact["opacities"] > 0.1 and exact["colors_precomp"] < 1e-6, exact
+
+
+def test_oracle_cov3d_precomp_gradient_matches_autograd():
+    """dL/dcov3D of the precomputed-covariance path (backward.cu:143-293 writes it with the
+    off-diagonals doubled: each of S01, S02, S12 stands for two entries of the symmetric matrix)."""
+    from gaussiancity_b200.synthetic import uniform_scene
+    from oracle import torch_naive
+    s = uniform_scene(150, 48, 40, sh_degree=1, seed=5, bg=(0.0, 0.1, 0.2))
+    c = lambda t: t.numpy()
+    args = (c(s.view_matrix), c(s.proj_matrix), c(s.campos), 48, 40, s.tanfovx, s.tanfovy, c(s.bg))
+    a = oracle.forward(c(s.means3D), c(s.opacities), c(s.scales), c(s.rotations), *args, shs=c(s.shs),
+                       sh_degree=1, precision="f64")
+    cov32 = a.cov3D.astype(np.float32)
+    b = oracle.forward(c(s.means3D), c(s.opacities), None, None, *args, shs=c(s.shs), sh_degree=1,
+                       cov3D_precomp=cov32, precision="f64")
+    G = np.random.default_rng(1).standard_normal((3, 40, 48))
+    g = oracle.backward(b, G)
+    leaf = torch.from_numpy(cov32).to(torch.float64).requires_grad_(True)
+    col, _ = torch_naive.render_autograd(s, cov3D=leaf)
+    (col * torch.from_numpy(G)).sum().backward()
+    assert np.abs(col.detach().numpy() - b.color).max() < 1e-6
+    y = g["dL_dcov3D"]
+    assert np.linalg.norm(y) > 0 and np.linalg.norm(leaf.grad.numpy() - y) / np.linalg.norm(y) < 1e-5
