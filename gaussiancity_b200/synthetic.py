@@ -51,7 +51,11 @@ def synthetic_camera(img_w, img_h, fovx_deg=60.0, znear=0.01, zfar=100.0, device
 
 
 def uniform_scene(P, img_w, img_h, sh_degree=0, seed=0, device="cpu", use_sh=True,
-                  sigma_px=(0.5, 4.0), bg=(0.0, 0.0, 0.0)):
+                  sigma_px=(0.5, 4.0), bg=(0.0, 0.0, 0.0), spread=1.1):
+    """SURVEY 8d "uniform" cloud.  `spread` = lateral extent in units of tan(fov/2) (1.1: ~17 % of the
+    centres fall outside the image); with spread > 1.3 and large `sigma_px` some splats whose
+    view-space x/z, y/z is CLAMPED to +-1.3 tan(fov/2) (forward.cu:80-85, backward.cu x_grad_mul)
+    still reach the screen -- the case the default never produces."""
     g = torch.Generator(device="cpu").manual_seed(seed)
 
     def U(*shape, lo=0.0, hi=1.0):
@@ -63,8 +67,8 @@ def uniform_scene(P, img_w, img_h, sh_degree=0, seed=0, device="cpu", use_sh=Tru
     tanfovx, tanfovy, view, proj, campos = synthetic_camera(img_w, img_h, device=device)
     focal = img_w / (2.0 * tanfovx)
     z = U(P, lo=2.0, hi=20.0)
-    x = U(P, lo=-1.0, hi=1.0) * z * tanfovx * 1.1
-    y = U(P, lo=-1.0, hi=1.0) * z * tanfovy * 1.1
+    x = U(P, lo=-1.0, hi=1.0) * z * tanfovx * spread
+    y = U(P, lo=-1.0, hi=1.0) * z * tanfovy * spread
     means = torch.stack([x, y, z], dim=1)
     lo, hi = math.log(sigma_px[0]), math.log(sigma_px[1])
     sig = torch.exp(U(P, lo=lo, hi=hi))

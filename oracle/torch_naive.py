@@ -37,7 +37,7 @@ def _sh_to_rgb(deg, shs, dirs):
     return torch.clamp_min(res + 0.5, 0.0)
 
 
-def _preprocess(s, dt, cov3D=None):
+def _preprocess(s, dt, cov3D=None, reference_clamp_gradient=True):
     """Per-Gaussian forward quantities (DGR forward.cu:147-233), vectorised over Gaussians, in dtype
     `dt`; differentiable w.r.t. any input tensor of `s` that requires grad."""
     P, W, H = s.means3D.shape[0], s.img_w, s.img_h
@@ -69,6 +69,13 @@ def _preprocess(s, dt, cov3D=None):
     tzs = torch.where(visible, tz, torch.ones_like(tz))
     tx = torch.clamp(view[:, 0] / tzs, -limx, limx) * tzs
     ty = torch.clamp(view[:, 1] / tzs, -limy, limy) * tzs
+    if reference_clamp_gradient:
+        # backward.cu:170-171,278-279 (x_grad_mul / y_grad_mul): a clamped t.x, t.y is a CONSTANT for
+        # the reference's backward -- not even its dependence on t.z (= +-lim * t.z) is propagated
+        inx = (view[:, 0] / tzs).detach().abs() <= limx
+        iny = (view[:, 1] / tzs).detach().abs() <= limy
+        tx = torch.where(inx, view[:, 0], tx.detach())
+        ty = torch.where(iny, view[:, 1], ty.detach())
     zero = torch.zeros_like(tzs)
     J = torch.stack([torch.stack([fx / tzs, zero, -fx * tx / (tzs * tzs)], dim=1),
                      torch.stack([zero, fy / tzs, -fy * ty / (tzs * tzs)], dim=1)], dim=1)   # [P,2,3]
@@ -136,7 +143,8 @@ def render_naive(s):
     return C + Tr[None] * s.bg.to(f32)[:, None, None], q["radii"]
 
 
-def render_autograd(s, dtype=torch.float64, reference_cap_gradient=True, cov3D=None):
+def render_autograd(s, dtype=torch.float64, reference_cap_gradient=True, cov3D=None,
+                    reference_clamp_gradient=True):
     """Differentiable restatement for gradient ground truth (SURVEY 8c "fp64 + autograd"): the same
     forward written functionally (no in-place updates), so torch.autograd differentiates it.  The
     thresholds (alpha < 1/255, T < 1e-4, the frustum clamp of t, the SH clamp at 0) are piecewise
@@ -145,11 +153,13 @@ def render_autograd(s, dtype=torch.float64, reference_cap_gradient=True, cov3D=N
     `alpha = min(0.99, o G)` but propagates `dL/dalpha` to G and o as if the cap were not there, so
     with `reference_cap_gradient=True` the cap is applied straight-through (capped value, identity
     gradient); with False the mathematically exact derivative (zero where capped) is taken -- the two
-    differ wherever o G > 0.99, i.e. all over GaussianCity's opacity-1 scenes.  Returns (color[3,H,W], ndc[P,2]); `ndc` is the retained intermediate whose
+    differ wherever o G > 0.99, i.e. all over GaussianCity's opacity-1 scenes.  Likewise
+    `reference_clamp_gradient` (see _preprocess): a frustum-clamped t.x / t.y is a constant for the
+    reference's backward.  Returns (color[3,H,W], ndc[P,2]); `ndc` is the retained intermediate whose
     gradient is the reference's `dL_dmeans2D` ("viewspace points").  Small scenes only: every
     Gaussian touches a full-image tensor."""
     W, H = s.img_w, s.img_h
-    q = _preprocess(s, dtype, cov3D=cov3D)
+    q = _preprocess(s, dtype, cov3D=cov3D, reference_clamp_gradient=reference_clamp_gradient)
     if q["ndc"].requires_grad:
         q["ndc"].retain_grad()
     px, py, conic, rgb, opac = q["px"], q["py"], q["conic"], q["rgb"], q["opac"]

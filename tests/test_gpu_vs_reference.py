@@ -116,3 +116,35 @@ def test_mark_visible_matches_reference(ref, built_lib, cuda_device):
     a = ours.mark_visible(m, s.view_matrix, s.proj_matrix)
     b = ref.mark_visible(m, s.view_matrix, s.proj_matrix)
     assert a.dtype == torch.bool and torch.equal(a, b)
+
+
+def test_frustum_clamped_splats_match_reference(ref, built_lib, cuda_device):
+    """Splats clamped to +-1.3 tan(fov/2) in computeCov2D (forward.cu:80-85; x_grad_mul in
+    backward.cu:170-171) that still reach the screen -- a wide cloud of large splats, which the
+    other configurations never produce.  Same bars: forward bit-exact, gradients <= 1e-4."""
+    P, W, H = 20_000, 320, 200
+    s = uniform_scene(P, W, H, sh_degree=1, seed=21, device=cuda_device, sigma_px=(6, 30), spread=2.0,
+                      bg=(0.1, 0.2, 0.3))
+    m = s.means3D
+    clamped = ((m[:, 0] / m[:, 2]).abs() > 1.3 * s.tanfovx) | ((m[:, 1] / m[:, 2]).abs() > 1.3 * s.tanfovy)
+    args = refext.scene_forward_args(s)
+    R_ref, col_ref, radii_ref, geom_ref, bin_ref, img_ref = ref.rasterize_gaussians(*args)
+    R, col, radii, geom, binning, img = ours.rasterize_gaussians(*args)
+    torch.cuda.synchronize()
+    assert int((clamped & (radii_ref > 0)).sum()) > 1000
+    assert R == R_ref and torch.equal(radii, radii_ref)
+    assert torch.equal(col, col_ref), f"colour differs at {(col != col_ref).sum().item()} elements"
+    g = torch.Generator(device="cpu").manual_seed(5)
+    grad_out = torch.randn(3, H, W, generator=g).to(cuda_device)
+    gr = ref.rasterize_gaussians_backward(*refext.scene_backward_args(s, radii_ref, grad_out, geom_ref, R_ref, bin_ref, img_ref))
+    go = ours.rasterize_gaussians_backward(*refext.scene_backward_args(s, radii, grad_out, geom, R, binning, img))
+    torch.cuda.synchronize()
+    for n, a, b in zip(["dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dcov3D", "dL_dsh",
+                        "dL_dscales", "dL_drotations"], go, gr):
+        if b.numel() == 0:
+            continue
+        assert torch.isfinite(a).all(), n
+        assert _relerr(a, b) <= 1e-4, f"{n} norm-relative error {_relerr(a, b)}"
+        # and specifically on the clamped splats
+        if a.shape[0] == P and b[clamped].double().norm() > 0:
+            assert _relerr(a[clamped], b[clamped]) <= 1e-4, f"{n} on clamped splats: {_relerr(a[clamped], b[clamped])}"
