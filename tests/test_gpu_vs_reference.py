@@ -148,3 +148,38 @@ def test_frustum_clamped_splats_match_reference(ref, built_lib, cuda_device):
         # and specifically on the clamped splats
         if a.shape[0] == P and b[clamped].double().norm() > 0:
             assert _relerr(a[clamped], b[clamped]) <= 1e-4, f"{n} on clamped splats: {_relerr(a[clamped], b[clamped])}"
+
+
+def test_near_plane_culls_and_sh_clamps_match_reference(ref, built_lib, cuda_device):
+    """A third of the points at or behind the z_view <= 0.2 cull, SH colours driven negative so the
+    `max(rgb + 0.5, 0)` clamp fires on many channels (flags recorded forward, gradients zeroed
+    backward): forward bit-exact incl. the flags, gradients <= 1e-4."""
+    P, W, H = 30_000, 400, 240
+    s = uniform_scene(P, W, H, sh_degree=2, seed=33, device=cuda_device, bg=(0.2, 0.1, 0.0))
+    m = s.means3D.clone()
+    m[::3, 2] = torch.linspace(-3.0, 0.25, m[::3].shape[0], device=cuda_device)
+    s = s._replace(means3D=m.contiguous(), shs=(s.shs * 4.0).contiguous())
+    args = refext.scene_forward_args(s)
+    R_ref, col_ref, radii_ref, geom_ref, bin_ref, img_ref = ref.rasterize_gaussians(*args)
+    R, col, radii, geom, binning, img = ours.rasterize_gaussians(*args)
+    torch.cuda.synchronize()
+    vis = radii_ref > 0
+    assert int((~vis[::3]).sum()) > 9000 and int(vis.sum()) > 10_000
+    assert R == R_ref and torch.equal(radii, radii_ref) and torch.equal(col, col_ref)
+    gv = refext.ref_geom_views(geom_ref, P)
+    ov = refext.our_views(P, R, W, H, geom, binning, img)
+    cl = ov["clamped"][vis]
+    cl3 = torch.stack([(cl & 1) != 0, (cl & 2) != 0, (cl & 4) != 0], dim=1)
+    assert torch.equal(cl3, gv["clamped"][vis]) and cl3.float().mean().item() > 0.1
+    g = torch.Generator(device="cpu").manual_seed(6)
+    grad_out = torch.randn(3, H, W, generator=g).to(cuda_device)
+    gr = ref.rasterize_gaussians_backward(*refext.scene_backward_args(s, radii_ref, grad_out, geom_ref, R_ref, bin_ref, img_ref))
+    go = ours.rasterize_gaussians_backward(*refext.scene_backward_args(s, radii, grad_out, geom, R, binning, img))
+    torch.cuda.synchronize()
+    for n, a, b in zip(["dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dcov3D", "dL_dsh",
+                        "dL_dscales", "dL_drotations"], go, gr):
+        if b.numel() == 0:
+            continue
+        assert torch.isfinite(a).all(), n
+        assert _relerr(a, b) <= 1e-4, f"{n} norm-relative error {_relerr(a, b)}"
+        assert (a[~vis] == 0).all(), f"{n} non-zero for culled Gaussians"

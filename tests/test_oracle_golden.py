@@ -251,3 +251,19 @@ def test_frustum_clamped_splats_forward_and_backward():
     assert max(err.values()) < 1e-6, err
     exact = _autograd_vs_oracle(s32, "shs", 0, reference_clamp_gradient=False)
     assert exact["means3D"] > 1e-3 and exact["scales"] < 1e-6, exact
+
+
+def test_near_plane_culls_and_sh_clamps_forward_and_backward():
+    """Two more paths the default clouds barely touch: a third of the points at or behind the
+    z_view <= 0.2 cull (auxiliary.h:145), and SH colours driven negative so `max(rgb + 0.5, 0)` clamps
+    on many channels (forward.cu:60-65 records the flags, backward.cu zeroes those gradients)."""
+    from gaussiancity_b200.synthetic import uniform_scene
+    s32 = uniform_scene(240, 80, 56, sh_degree=2, seed=13, bg=(0.2, 0.1, 0.0))
+    m = s32.means3D.clone()
+    m[::3, 2] = torch.linspace(-3.0, 0.25, m[::3].shape[0])      # behind / inside the near cull
+    s32 = s32._replace(means3D=m, shs=(s32.shs * 4.0).contiguous())
+    r = oracle.forward_scene(s32, "f64")
+    assert (r.radii[::3] == 0).sum() >= 70 and (r.radii > 0).sum() > 100
+    assert r.clamped[r.radii > 0].mean() > 0.1
+    err = _autograd_vs_oracle(s32, "shs", 3)
+    assert max(err.values()) < 1e-6, err
