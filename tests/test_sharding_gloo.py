@@ -1,4 +1,4 @@
-"""CPU, world_size 2, gloo: the collective plumbing of gaussiancity_b200.sharding
+"""CPU, world_size 2 and 3, gloo: the collective plumbing of gaussiancity_b200.sharding
 (broadcast -> per-rank tile rows -> image all_reduce; partial [P,12] accumulators ->
 reduce_scatter -> per-slice geometry backward -> optional all_gather), with the CPU oracle
 plugged in as the compute backend.  The sharded result must equal the unsharded oracle."""
@@ -92,9 +92,11 @@ def _worker(rank, world, port, P, W, H, outdir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("P,W,H", [(301, 96, 80)])   # P not divisible by 2, H not a multiple of 16
-def test_two_rank_sharded_frame_equals_unsharded(tmp_path, P, W, H):
-    world = 2
+# P not divisible by the world size, H not a multiple of 16; 3 ranks over 5 tile rows; fewer
+# Gaussians than ranks (the last rank's geometry slice is empty)
+@pytest.mark.parametrize("P,W,H,world", [(301, 96, 80, 2), (301, 96, 80, 3), (2, 48, 48, 3)],
+                         ids=["w2", "w3", "w3_tiny"])
+def test_sharded_frame_equals_unsharded(tmp_path, P, W, H, world):
     mp.spawn(_worker, args=(world, _free_port(), P, W, H, str(tmp_path)), nprocs=world, join=True)
     s = uniform_scene(P, W, H, sh_degree=1, seed=31)
     r = oracle.forward_scene(s, "f32")
@@ -105,7 +107,9 @@ def test_two_rank_sharded_frame_equals_unsharded(tmp_path, P, W, H):
                dL_dcov3D=g["dL_dcov3D"], dL_dsh=g["dL_dsh"], dL_dscales=g["dL_dscale"], dL_drotations=g["dL_drot"])
     outs = [np.load(tmp_path / f"rank{k}.npz") for k in range(world)]
     slices = sorted((int(o["start"]), int(o["count"])) for o in outs)
-    assert slices[0][0] == 0 and slices[0][0] + slices[0][1] == slices[1][0] and slices[1][0] + slices[1][1] == P
+    assert slices[0][0] == 0 and sum(c for _, c in slices) == P
+    for (s0, c0), (s1, _) in zip(slices, slices[1:]):
+        assert s0 + c0 == s1
     for o in outs:
         # disjoint rows + x+0 exact => the assembled frame is bit-identical on every rank
         assert np.array_equal(o["color"], r.color)
