@@ -104,17 +104,17 @@ def our_views(P, R, W, H, geom, binning, img):
     return v
 
 
-def scene_forward_args(s):
+def scene_forward_args(s, scale_modifier=1.0):
     """Positional args of rasterize_gaussians (DGR/bindings.cpp:16) for a Scene."""
     e = torch.Tensor([])
     return (s.bg, s.means3D, s.colors_precomp if s.colors_precomp is not None else e, s.opacities,
-            s.scales, s.rotations, 1.0, e, s.view_matrix, s.proj_matrix, s.tanfovx, s.tanfovy,
+            s.scales, s.rotations, scale_modifier, e, s.view_matrix, s.proj_matrix, s.tanfovx, s.tanfovy,
             s.img_h, s.img_w, s.shs if s.shs is not None else e, s.sh_degree, s.campos, False, False)
 
 
-def scene_backward_args(s, radii, grad_out, geom, R, binning, img):
+def scene_backward_args(s, radii, grad_out, geom, R, binning, img, scale_modifier=1.0):
     e = torch.Tensor([])
     return (s.bg, s.means3D, radii, s.colors_precomp if s.colors_precomp is not None else e,
-            s.scales, s.rotations, 1.0, e, s.view_matrix, s.proj_matrix, s.tanfovx, s.tanfovy,
+            s.scales, s.rotations, scale_modifier, e, s.view_matrix, s.proj_matrix, s.tanfovx, s.tanfovy,
             grad_out, s.shs if s.shs is not None else e, s.sh_degree, s.campos, geom, R, binning,
             img, False)

@@ -153,13 +153,15 @@ def test_frustum_clamped_splats_match_reference(ref, built_lib, cuda_device):
 def test_near_plane_culls_and_sh_clamps_match_reference(ref, built_lib, cuda_device):
     """A third of the points at or behind the z_view <= 0.2 cull, SH colours driven negative so the
     `max(rgb + 0.5, 0)` clamp fires on many channels (flags recorded forward, gradients zeroed
-    backward): forward bit-exact incl. the flags, gradients <= 1e-4."""
+    backward), and a scale_modifier != 1 (the reference returns dL_dscale w.r.t. the modified
+    scale, backward.cu:297-345): forward bit-exact incl. the flags, gradients <= 1e-4."""
     P, W, H = 30_000, 400, 240
     s = uniform_scene(P, W, H, sh_degree=2, seed=33, device=cuda_device, bg=(0.2, 0.1, 0.0))
     m = s.means3D.clone()
     m[::3, 2] = torch.linspace(-3.0, 0.25, m[::3].shape[0], device=cuda_device)
     s = s._replace(means3D=m.contiguous(), shs=(s.shs * 4.0).contiguous())
-    args = refext.scene_forward_args(s)
+    MOD = 1.75                                     # scale_modifier != 1 (no other GPU test uses one)
+    args = refext.scene_forward_args(s, scale_modifier=MOD)
     R_ref, col_ref, radii_ref, geom_ref, bin_ref, img_ref = ref.rasterize_gaussians(*args)
     R, col, radii, geom, binning, img = ours.rasterize_gaussians(*args)
     torch.cuda.synchronize()
@@ -173,8 +175,8 @@ def test_near_plane_culls_and_sh_clamps_match_reference(ref, built_lib, cuda_dev
     assert torch.equal(cl3, gv["clamped"][vis]) and cl3.float().mean().item() > 0.1
     g = torch.Generator(device="cpu").manual_seed(6)
     grad_out = torch.randn(3, H, W, generator=g).to(cuda_device)
-    gr = ref.rasterize_gaussians_backward(*refext.scene_backward_args(s, radii_ref, grad_out, geom_ref, R_ref, bin_ref, img_ref))
-    go = ours.rasterize_gaussians_backward(*refext.scene_backward_args(s, radii, grad_out, geom, R, binning, img))
+    gr = ref.rasterize_gaussians_backward(*refext.scene_backward_args(s, radii_ref, grad_out, geom_ref, R_ref, bin_ref, img_ref, scale_modifier=MOD))
+    go = ours.rasterize_gaussians_backward(*refext.scene_backward_args(s, radii, grad_out, geom, R, binning, img, scale_modifier=MOD))
     torch.cuda.synchronize()
     for n, a, b in zip(["dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dcov3D", "dL_dsh",
                         "dL_dscales", "dL_drotations"], go, gr):

@@ -288,3 +288,25 @@ def test_oracle_is_equivariant_under_gaussian_permutation():
     for k in ("dL_dmean3D", "dL_dopacity", "dL_dscale", "dL_drot", "dL_dsh", "dL_dmean2D"):
         x, y = ga[k][perm.numpy()].astype(np.float64), gb[k].astype(np.float64)   # fp32 sums in another order
         assert np.linalg.norm(x - y) <= 1e-5 * np.linalg.norm(x), k
+
+
+def test_scale_modifier_gradient_chain_rule():
+    """scale_modifier m multiplies the scales inside computeCov3D (forward.cu:113-118), so with
+    s' = s / m the frame is the same.  Reference quirk, reproduced by oracle and CUDA path: the
+    returned dL_dscale is the gradient w.r.t. the MODIFIED scale m s' -- backward.cu:297-345 rebuilds
+    M from `mod * scale` but never multiplies dL_dscale by `mod` -- so it is the same array for
+    (s, m = 1) and (s / m, m), where the exact chain rule would give m times it."""
+    from gaussiancity_b200.synthetic import uniform_scene
+    s = uniform_scene(600, 96, 64, sh_degree=1, seed=23)
+    c = lambda t: t.numpy()
+    args = (c(s.view_matrix), c(s.proj_matrix), c(s.campos), 96, 64, s.tanfovx, s.tanfovy, c(s.bg))
+    kw = dict(shs=c(s.shs), sh_degree=1, precision="f64")
+    a = oracle.forward(c(s.means3D), c(s.opacities), c(s.scales), c(s.rotations), *args, **kw)
+    b = oracle.forward(c(s.means3D), c(s.opacities), c(s.scales) * 0.25, c(s.rotations), *args,
+                       scale_modifier=4.0, **kw)                  # 0.25 and 4 are exact in binary
+    assert np.array_equal(a.radii, b.radii) and np.allclose(a.color, b.color, atol=1e-12)
+    G = np.random.default_rng(3).standard_normal((3, 64, 96))
+    ga, gb = oracle.backward(a, G), oracle.backward(b, G)
+    assert np.abs(ga["dL_dscale"]).max() > 0
+    for k in ("dL_dscale", "dL_dmean3D", "dL_drot", "dL_dopacity", "dL_dsh"):
+        assert np.allclose(ga[k], gb[k], rtol=1e-9, atol=1e-12), k
