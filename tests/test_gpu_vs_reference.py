@@ -212,3 +212,38 @@ def test_full_size_permutation_equivariance(built_lib, cuda_device):
         if b.numel() == 0:
             continue
         assert _relerr(a[perm], b) <= 1e-4, f"{n}: {_relerr(a[perm], b)}"
+
+
+def test_cov3d_precomp_path_matches_reference(ref, built_lib, cuda_device):
+    """cov3D_precomp instead of scales + rotations (forward.cu:184-190, backward.cu:416-424): the
+    covariances are the reference's own (read back from its geometry buffer), forward bit-exact,
+    dL_dcov3D and the rest <= 1e-4, dL_dscales / dL_drotations untouched (zeros)."""
+    P, W, H = 40_000, 384, 256
+    s = uniform_scene(P, W, H, sh_degree=1, seed=51, device=cuda_device, bg=(0.0, 0.1, 0.2))
+    out0 = ref.rasterize_gaussians(*refext.scene_forward_args(s))
+    cov = refext.ref_geom_views(out0[3], P)["cov3D"].clone().contiguous()
+    e = torch.Tensor([])
+    fargs = (s.bg, s.means3D, e, s.opacities, e, e, 1.0, cov, s.view_matrix, s.proj_matrix, s.tanfovx,
+             s.tanfovy, H, W, s.shs, s.sh_degree, s.campos, False, False)
+    R_ref, col_ref, radii_ref, geom_ref, bin_ref, img_ref = ref.rasterize_gaussians(*fargs)
+    R, col, radii, geom, binning, img = ours.rasterize_gaussians(*fargs)
+    torch.cuda.synchronize()
+    assert R == R_ref == out0[0] and torch.equal(radii, radii_ref) and torch.equal(col, col_ref)
+    assert torch.equal(col_ref, out0[1])
+    grad_out = torch.randn(3, H, W, generator=torch.Generator().manual_seed(9)).to(cuda_device)
+    bargs = lambda rad, gm, r_, bn, im: (s.bg, s.means3D, rad, e, e, e, 1.0, cov, s.view_matrix, s.proj_matrix,
+                                        s.tanfovx, s.tanfovy, grad_out, s.shs, s.sh_degree, s.campos, gm, r_,
+                                        bn, im, False)
+    gr = ref.rasterize_gaussians_backward(*bargs(radii_ref, geom_ref, R_ref, bin_ref, img_ref))
+    go = ours.rasterize_gaussians_backward(*bargs(radii, geom, R, binning, img))
+    torch.cuda.synchronize()
+    names = ["dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dcov3D", "dL_dsh",
+             "dL_dscales", "dL_drotations"]
+    for n, a, b in zip(names, go, gr):
+        assert a.shape == b.shape, n
+        if b.numel() == 0:
+            continue
+        if n in ("dL_dscales", "dL_drotations"):
+            assert bool((a == 0).all()) and bool((b == 0).all()), n
+        else:
+            assert _relerr(a, b) <= 1e-4, f"{n}: {_relerr(a, b)}"
