@@ -247,3 +247,23 @@ def test_cov3d_precomp_path_matches_reference(ref, built_lib, cuda_device):
             assert bool((a == 0).all()) and bool((b == 0).all()), n
         else:
             assert _relerr(a, b) <= 1e-4, f"{n}: {_relerr(a, b)}"
+
+
+def test_active_sh_degree_below_coefficient_count_matches_reference(ref, built_lib, cuda_device):
+    """Degree 1 evaluated on [P,16,3] coefficients (3DGS-style progressive SH; D < sqrt(M) - 1):
+    forward bit-exact, dL_dsh matches on the 4 active coefficients and is exactly zero on the rest."""
+    P, W, H = 50_000, 400, 300
+    s = uniform_scene(P, W, H, sh_degree=3, seed=61, device=cuda_device)._replace(sh_degree=1)
+    R_ref, col_ref, radii_ref, geom_ref, bin_ref, img_ref = ref.rasterize_gaussians(*refext.scene_forward_args(s))
+    R, col, radii, geom, binning, img = ours.rasterize_gaussians(*refext.scene_forward_args(s))
+    torch.cuda.synchronize()
+    assert R == R_ref and torch.equal(radii, radii_ref) and torch.equal(col, col_ref)
+    grad_out = torch.randn(3, H, W, generator=torch.Generator().manual_seed(10)).to(cuda_device)
+    gr = ref.rasterize_gaussians_backward(*refext.scene_backward_args(s, radii_ref, grad_out, geom_ref, R_ref, bin_ref, img_ref))
+    go = ours.rasterize_gaussians_backward(*refext.scene_backward_args(s, radii, grad_out, geom, R, binning, img))
+    torch.cuda.synchronize()
+    for n, a, b in zip(["dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dcov3D", "dL_dsh",
+                        "dL_dscales", "dL_drotations"], go, gr):
+        assert a.shape == b.shape, n
+        assert _relerr(a, b) <= 1e-4, f"{n}: {_relerr(a, b)}"
+    assert go[5].shape == (P, 16, 3) and bool((go[5][:, 4:] == 0).all()) and bool((gr[5][:, 4:] == 0).all())
