@@ -117,10 +117,10 @@ def tile_sort_passes(W, H):
 
 
 def kernels_per_step(W, H, backward=True):
-    """Kernels of OUR library launched by one forward(+backward) (memsets excluded):
-    preprocess, depth sort (1 histogram + 4 onesweep passes), scan (3), emit, tile sort
-    (1 histogram + passes), ranges+gather, blend_fwd [+ blend_bwd, geometry_bwd]."""
-    fwd = 1 + (1 + 4) + 3 + 1 + (1 + tile_sort_passes(W, H)) + 1 + 1
+    """Kernels of OUR library launched by one forward(+backward) (memsets / copies excluded):
+    preprocess, depth sort (1 histogram + 4 onesweep passes), scan+emit, tile sort passes,
+    tile ranges, blend_fwd [+ blend_bwd, geometry_bwd]."""
+    fwd = 1 + (1 + 4) + 1 + tile_sort_passes(W, H) + 1 + 1
     return fwd + (2 if backward else 0)
 
 

@@ -17,10 +17,17 @@ EXPORTED_SYMBOLS = (
     "gcr_abi_version",
     "gcr_last_error",
     "gcr_rasterizer_forward",
+    "gcr_rasterizer_forward_striped",
     "gcr_rasterizer_backward",
     "gcr_rasterizer_backward_blend",
     "gcr_rasterizer_backward_geometry",
     "gcr_rasterizer_mark_visible",
+    "gcr_stripe_partition",
+    "gcr_peer_alloc",
+    "gcr_peer_open",
+    "gcr_peer_close",
+    "gcr_peer_free",
+    "gcr_peer_barrier",
     "gcr_debug_offset",
     "gcr_debug_set_cov3d_out",
     "gcr_profile_enable",
@@ -31,8 +38,12 @@ EXPORTED_SYMBOLS = (
 
 # enum values of gcr_debug_offset (include/gcr_rasterizer.h)
 GEOM_DEPTH_SORTED_KEYS, GEOM_TILES_TOUCHED, GEOM_RECORDS, GEOM_CLAMPED = 0, 1, 2, 3
-GEOM_SORTED_GAUSS, GEOM_OFFSETS, GEOM_GRAD_ACC, GEOM_RADII, GEOM_TOTAL_BYTES = 4, 5, 6, 7, 100
-BIN_POINT_LIST, BIN_TILE_KEYS, BIN_INSTANCES, BIN_TOTAL_BYTES = 200, 201, 202, 300
+GEOM_SORTED_GAUSS, GEOM_OFFSETS, GEOM_GRAD_ACC, GEOM_RADII, GEOM_OWNER, GEOM_COUNTERS = 4, 5, 6, 7, 8, 9
+GEOM_TOTAL_BYTES = 100
+BIN_POINT_LIST, BIN_TILE_KEYS, BIN_TOTAL_BYTES = 200, 201, 300
+ABI_VERSION = 2          # GCR_ABI_VERSION
+MAX_SHARDS = 16          # GCR_MAX_SHARDS
+PEER_HANDLE_BYTES = 64   # GCR_PEER_HANDLE_BYTES
 IMG_FINAL_T, IMG_N_CONTRIB, IMG_RANGES, IMG_TOTAL_BYTES = 400, 401, 402, 500
 
 _lib = None
@@ -48,22 +59,38 @@ def _declare(l):
     l.gcr_abi_version.argtypes = []
     l.gcr_last_error.restype = ctypes.c_char_p
     l.gcr_last_error.argtypes = []
+    fwd_args = ([ALLOC_FN, c_void_p] * 3 + [c_int] * 3 + [c_void_p, c_int, c_int] +
+                [c_void_p] * 5 + [c_float] + [c_void_p] * 5 + [c_float, c_float, c_int] +
+                [c_void_p, c_void_p, c_int, c_int, c_int])
     l.gcr_rasterizer_forward.restype = c_int
-    l.gcr_rasterizer_forward.argtypes = (
-        [ALLOC_FN, c_void_p] * 3 + [c_int] * 3 + [c_void_p, c_int, c_int] +
-        [c_void_p] * 5 + [c_float] + [c_void_p] * 5 + [c_float, c_float, c_int] +
-        [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p])
+    l.gcr_rasterizer_forward.argtypes = fwd_args + [c_void_p]
+    l.gcr_rasterizer_forward_striped.restype = c_int
+    l.gcr_rasterizer_forward_striped.argtypes = fwd_args + [c_void_p, c_void_p]
     l.gcr_rasterizer_backward.restype = c_int
     l.gcr_rasterizer_backward.argtypes = (
         [c_int] * 4 + [c_void_p, c_int, c_int] + [c_void_p] * 4 + [c_float] + [c_void_p] * 5 +
         [c_float, c_float] + [c_void_p] * 14 + [c_int, c_int, c_int, c_void_p])
     l.gcr_rasterizer_backward_blend.restype = c_int
     l.gcr_rasterizer_backward_blend.argtypes = (
-        [c_int, c_int, c_void_p, c_int, c_int] + [c_void_p] * 4 + [c_int, c_int, c_int, c_void_p])
+        [c_int, c_int, c_void_p, c_int, c_int] + [c_void_p] * 4 + [ctypes.POINTER(c_void_p)] +
+        [c_int] * 6 + [c_void_p])
     l.gcr_rasterizer_backward_geometry.restype = c_int
     l.gcr_rasterizer_backward_geometry.argtypes = (
         [c_int] * 3 + [c_void_p] * 3 + [c_float] + [c_void_p] * 5 + [c_int, c_int, c_float, c_float] +
-        [c_void_p] * 12 + [c_int, c_int, c_int, c_void_p])
+        [c_void_p] * 12 + [c_int] * 6 + [c_void_p])
+    l.gcr_stripe_partition.restype = c_int
+    l.gcr_stripe_partition.argtypes = ([c_int, c_void_p, c_void_p, c_float] + [c_void_p] * 4 +
+                                       [c_int, c_int, c_float, c_float, c_int] + [c_void_p] * 3)
+    l.gcr_peer_alloc.restype = c_int
+    l.gcr_peer_alloc.argtypes = [c_size_t, ctypes.POINTER(c_void_p), ctypes.POINTER(ctypes.c_ubyte)]
+    l.gcr_peer_open.restype = c_int
+    l.gcr_peer_open.argtypes = [ctypes.POINTER(ctypes.c_ubyte), ctypes.POINTER(c_void_p)]
+    l.gcr_peer_close.restype = c_int
+    l.gcr_peer_close.argtypes = [c_void_p]
+    l.gcr_peer_free.restype = c_int
+    l.gcr_peer_free.argtypes = [c_void_p]
+    l.gcr_peer_barrier.restype = c_int
+    l.gcr_peer_barrier.argtypes = [ctypes.POINTER(c_void_p), c_int, c_int, ctypes.c_uint, c_void_p]
     l.gcr_rasterizer_mark_visible.restype = c_int
     l.gcr_rasterizer_mark_visible.argtypes = [c_int] + [c_void_p] * 5
     l.gcr_debug_offset.restype = c_size_t

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libgcr_rasterizer.so")
 STAMP = os.path.join(PKG_DIR, ".libgcr_rasterizer.stamp")
 
 SOURCES = ["api.cu", "preprocess.cu", "binning.cu", "blend_fwd.cu", "blend_bwd.cu",
-           "preprocess_bwd.cu"]
+           "preprocess_bwd.cu", "peer.cu"]
 HEADERS = ["gcr_common.cuh", "gcr_kernels.h", "blend_common.cuh",
            os.path.join(ROOT, "include", "gcr_rasterizer.h")]
 

@@ -6,29 +6,25 @@
 // T (1 - alpha) < 1e-4; C += rgb alpha T.  Outputs colour (CHW) = C + T bg, final_T, n_contrib
 // (1-based list position of the last contributor).
 //
-// B200 design (not the reference's): the tile's instance records are contiguous in HBM
-// (binning.cu gathers them in sorted order), so each batch of 256 records (12 KB) is staged
-// into shared memory by ONE TMA bulk copy (cp.async.bulk -> UBLKCP) into a 2-stage ring that
-// is refilled while the previous batch is being blended (mbarrier complete_tx signalling, no
-// per-thread gather loads).  Each warp owns an 8x4 pixel sub-rectangle: lanes first test 32
-// records at a time against that sub-rectangle (exact-conservative ellipse/rect test,
-// blend_common.cuh), ballot, and only the surviving records are evaluated per pixel.  A warp
-// whose 32 pixels have all saturated (T < 1e-4) stops evaluating; the CTA leaves when all
-// eight have (block vote once per batch).  Arithmetic per pixel is pinned to the reference's
-// SASS order (gcr_power, expf, fma order of the colour accumulation), so final_T / n_contrib
-// are bit-identical.
-#include <cstdlib>
+// B200 design (not the reference's): a tile's list is walked in batches of 256 instances through
+// a 2-stage shared-memory ring.  Each thread fetches ONE instance of the next batch straight from
+// the per-Gaussian record array -- its id from point_list one batch ahead, then three 16-byte
+// asynchronous copies (cp.async -> LDGSTS, no register staging) whose completion is signalled
+// on the stage's mbarrier (cp.async.mbarrier.arrive) -- while the current batch is blended.
+// Only batches a tile actually reaches are ever fetched: tiles saturate after ~20 % of their
+// list on the headline workload, so this replaced a 48 B x R materialisation pass that wrote
+// (and re-read) 2.5x more than the blend consumes (profiles/r02_*).  Each warp owns an 8x4
+// pixel sub-rectangle: lanes first test 32 records at a time against that sub-rectangle
+// (exact-conservative ellipse/rect test, blend_common.cuh), ballot, and only the surviving
+// records are evaluated per pixel.  A warp whose 32 pixels have all saturated (T < 1e-4) stops
+// evaluating; the CTA leaves when all eight have (block vote once per batch).  Arithmetic per
+// pixel is pinned to the reference's SASS order (gcr_power, expf, fma order of the colour
+// accumulation), so final_T / n_contrib are bit-identical.
 #include "blend_common.cuh"
 #include "gcr_kernels.h"
 
 namespace {
 
-// kTrim (experimental, env GCR_BLEND_FWD=trim; not yet run on hardware): the ncu source view
-// counts 52 SASS instructions per surviving (warp, record); this variant folds the loop-invariant
-// parts of the record address and of the list position out of the survivor loop; nvcc then also
-// if-converts the state update (no inner branch): 49 instructions, identical arithmetic.  (Holding
-// libdevice's expf constants in registers was tried too: ptxas re-materialises them regardless.)
-template <bool kTrim>
 __global__ void __launch_bounds__(kBlendThreads)
 blend_fwd_kernel(GcrBlendArgs a) {
   __shared__ __align__(128) GcrRecord stage[kBlendStages][kBlendBatch];
@@ -36,7 +32,11 @@ blend_fwd_kernel(GcrBlendArgs a) {
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile_x = blockIdx.x;
-  const int tile_y = a.shard_rank + (int)blockIdx.y * a.shard_count;
+  int tile_y = (int)blockIdx.y;
+  if (a.stripe != nullptr) {
+    tile_y += a.stripe[0];
+    if (tile_y >= a.stripe[1]) return;   // grid covers every row; the stripe is device-side
+  }
   const uint2 range = a.ranges[tile_y * a.grid_x + tile_x];
   const int n = (int)(range.y - range.x);
   const int nb = (n + kBlendBatch - 1) / kBlendBatch;
@@ -51,20 +51,17 @@ blend_fwd_kernel(GcrBlendArgs a) {
   const float ry0 = (float)sub_y0, ry1 = (float)(sub_y0 + 3);
 
   if (tid == 0) {
-    gcr_mbar_init(&full_bar[0], 1);
-    gcr_mbar_init(&full_bar[1], 1);
+    gcr_mbar_init(&full_bar[0], kBlendThreads);
+    gcr_mbar_init(&full_bar[1], kBlendThreads);
     gcr_mbar_fence_init();
   }
   __syncthreads();
 
-  const GcrRecord* __restrict__ src = a.inst + range.x;
-  int issued = 0;
-  if (tid == 0 && nb > 0) {
-    const uint32_t bytes = (uint32_t)min(kBlendBatch, n) * (uint32_t)sizeof(GcrRecord);
-    gcr_mbar_expect_tx(&full_bar[0], bytes);
-    gcr_bulk_g2s(&stage[0][0], src, bytes, &full_bar[0]);
-    issued = 1;
-  }
+  const uint32_t* __restrict__ ids = a.point_list + range.x;
+  // batch 0 is fetched now; the id of this thread's instance in batch 1 rides in a register
+  if (nb > 0) gcr_gather_record(&stage[0][tid], a.records, tid < n ? (int)ids[tid] : -1, &full_bar[0]);
+  int next_id = (kBlendBatch + tid < n) ? (int)ids[kBlendBatch + tid] : -1;
+  int fetched = nb > 0 ? 1 : 0;   // batches whose copies this thread has issued
 
   float T = 1.0f;
   float C0 = 0.f, C1 = 0.f, C2 = 0.f;
@@ -74,13 +71,12 @@ blend_fwd_kernel(GcrBlendArgs a) {
   int b = 0;
   for (; b < nb; ++b) {
     const int s = b & 1;
-    if (tid == 0 && b + 1 < nb) {
+    if (b + 1 < nb) {
       // stage s^1 was last read in iteration b-1; the vote barrier at its end ordered those reads
-      const int start = (b + 1) * kBlendBatch;
-      const uint32_t bytes = (uint32_t)min(kBlendBatch, n - start) * (uint32_t)sizeof(GcrRecord);
-      gcr_mbar_expect_tx(&full_bar[s ^ 1], bytes);
-      gcr_bulk_g2s(&stage[s ^ 1][0], src + start, bytes, &full_bar[s ^ 1]);
-      issued = b + 2;
+      gcr_gather_record(&stage[s ^ 1][tid], a.records, next_id, &full_bar[s ^ 1]);
+      fetched = b + 2;
+      const int j = (b + 2) * kBlendBatch + tid;
+      next_id = j < n ? (int)ids[j] : -1;
     }
     gcr_mbar_wait(&full_bar[s], (uint32_t)((b >> 1) & 1));
 
@@ -97,56 +93,31 @@ blend_fwd_kernel(GcrBlendArgs a) {
           touch = gcr_subrect_touch(q0.x, q0.y, q0.z, q0.w, q1.x, twoL, rx0, rx1, ry0, ry1);
         }
         unsigned mask = __ballot_sync(0xffffffffu, touch);
-        if (kTrim) {
-          const GcrRecord* __restrict__ stc = st + g0;        // chunk-invariant parts hoisted
-          const uint32_t pos1 = (uint32_t)(b * kBlendBatch + g0 + 1);
-          while (mask) {
-            const int bit = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const GcrRecord* __restrict__ rec = stc + bit;
-            const float4 r0 = rec->q0;   // x, y, A, B   (broadcast LDS.128)
-            const float4 r1 = rec->q1;   // C, o, r, g
-            const float dx = __fsub_rn(r0.x, pxf);
-            const float dy = __fsub_rn(r0.y, pyf);
-            const float power = gcr_power(dx, dy, r0.z, r0.w, r1.x);
-            const float alpha = fminf(0.99f, __fmul_rn(r1.y, expf(power)));
-            const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
-            const bool ok = !done && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
-            const bool sat = ok && (test_T < 0.0001f);
-            done = done || sat;
-            if (ok && !sat) {
-              const float cb = rec->q2.x;  // b
-              C0 = __fmaf_rn(T, __fmul_rn(alpha, r1.z), C0);
-              C1 = __fmaf_rn(T, __fmul_rn(alpha, r1.w), C1);
-              C2 = __fmaf_rn(T, __fmul_rn(alpha, cb), C2);
-              T = test_T;
-              last_contributor = pos1 + (uint32_t)bit;
-            }
-          }
-        } else {
-          while (mask) {
-            const int jj = g0 + __ffs(mask) - 1;
-            mask &= mask - 1;
-            const float4 r0 = st[jj].q0;   // x, y, A, B   (broadcast LDS.128)
-            const float4 r1 = st[jj].q1;   // C, o, r, g
-            // straight-line evaluation, state updates predicated: same arithmetic as the reference
-            // on every contributing lane, no per-test branches (the warp is issue-bound)
-            const float dx = __fsub_rn(r0.x, pxf);
-            const float dy = __fsub_rn(r0.y, pyf);
-            const float power = gcr_power(dx, dy, r0.z, r0.w, r1.x);
-            const float alpha = fminf(0.99f, __fmul_rn(r1.y, expf(power)));
-            const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
-            const bool ok = !done && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
-            const bool sat = ok && (test_T < 0.0001f);
-            done = done || sat;
-            if (ok && !sat) {
-              const float cb = st[jj].q2.x;  // b
-              C0 = __fmaf_rn(T, __fmul_rn(alpha, r1.z), C0);
-              C1 = __fmaf_rn(T, __fmul_rn(alpha, r1.w), C1);
-              C2 = __fmaf_rn(T, __fmul_rn(alpha, cb), C2);
-              T = test_T;
-              last_contributor = (uint32_t)(b * kBlendBatch + jj + 1);
-            }
+        const GcrRecord* __restrict__ stc = st + g0;        // chunk-invariant parts hoisted
+        const uint32_t pos1 = (uint32_t)(b * kBlendBatch + g0 + 1);
+        while (mask) {
+          const int bit = __ffs(mask) - 1;
+          mask &= mask - 1;
+          const GcrRecord* __restrict__ rec = stc + bit;
+          const float4 r0 = rec->q0;   // x, y, A, B   (broadcast LDS.128)
+          const float4 r1 = rec->q1;   // C, o, r, g
+          // straight-line evaluation, state updates predicated: same arithmetic as the reference
+          // on every contributing lane, no per-test branches (the warp is issue-bound)
+          const float dx = __fsub_rn(r0.x, pxf);
+          const float dy = __fsub_rn(r0.y, pyf);
+          const float power = gcr_power(dx, dy, r0.z, r0.w, r1.x);
+          const float alpha = fminf(0.99f, __fmul_rn(r1.y, expf(power)));
+          const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+          const bool ok = !done && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+          const bool sat = ok && (test_T < 0.0001f);
+          done = done || sat;
+          if (ok && !sat) {
+            const float cb = rec->q2.x;  // b
+            C0 = __fmaf_rn(T, __fmul_rn(alpha, r1.z), C0);
+            C1 = __fmaf_rn(T, __fmul_rn(alpha, r1.w), C1);
+            C2 = __fmaf_rn(T, __fmul_rn(alpha, cb), C2);
+            T = test_T;
+            last_contributor = pos1 + (uint32_t)bit;
           }
         }
         if (__ballot_sync(0xffffffffu, !done) == 0u) break;  // warp saturated
@@ -159,8 +130,8 @@ blend_fwd_kernel(GcrBlendArgs a) {
       break;
     }
   }
-  // never exit with a bulk copy still in flight into this CTA's shared memory
-  if (tid == 0 && issued > b) gcr_mbar_wait(&full_bar[b & 1], (uint32_t)((b >> 1) & 1));
+  // never exit with this thread's asynchronous copies still in flight into shared memory
+  if (fetched > b) gcr_cp_async_wait_all();
 
   if (inside) {
     const int pix_id = a.W * pix_y + pix_x;
@@ -175,17 +146,9 @@ blend_fwd_kernel(GcrBlendArgs a) {
 
 }  // namespace
 
-void gcr_launch_blend_fwd(const GcrBlendArgs& a, cudaStream_t stream) {
-  const int rows = (a.grid_y - a.shard_rank + a.shard_count - 1) / a.shard_count;
-  if (rows <= 0 || a.grid_x <= 0) return;
-  dim3 grid(a.grid_x, rows, 1);
-  static const bool trim = [] {
-    const char* e = getenv("GCR_BLEND_FWD");
-    return e != nullptr && e[0] == 't';
-  }();
-  if (trim) {
-    blend_fwd_kernel<true><<<grid, kBlendThreads, 0, stream>>>(a);
-  } else {
-    blend_fwd_kernel<false><<<grid, kBlendThreads, 0, stream>>>(a);
-  }
+cudaError_t gcr_launch_blend_fwd(const GcrBlendArgs& a, cudaStream_t stream) {
+  if (a.grid_y <= 0 || a.grid_x <= 0) return cudaSuccess;
+  dim3 grid(a.grid_x, a.grid_y, 1);
+  blend_fwd_kernel<<<grid, kBlendThreads, 0, stream>>>(a);
+  return cudaGetLastError();
 }

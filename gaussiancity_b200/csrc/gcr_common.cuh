@@ -114,6 +114,26 @@ __forceinline__ __device__ void gcr_bulk_g2s(void* dst_smem, const void* src_gme
       : "memory");
 }
 
+// Asynchronous gather of ONE 48-byte record into shared memory: three 16-byte cp.async (SASS
+// LDGSTS.E.BYPASS.128: global -> shared without a register round trip, L2 only), then an
+// arrive-on-completion on `bar` (cp.async.mbarrier.arrive.noinc: the arrival counts against the
+// barrier's expected count, which is the number of participating threads).  id < 0: nothing to
+// fetch, the thread only arrives.  Every participating thread calls this once per phase.
+__forceinline__ __device__ void gcr_gather_record(GcrRecord* dst_smem, const GcrRecord* records, int id,
+                                                  uint64_t* bar) {
+  if (id >= 0) {
+    const uint32_t d = gcr_smem_u32(dst_smem);
+    const char* src = reinterpret_cast<const char*>(records + id);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 16), "l"(src + 16) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 32), "l"(src + 32) : "memory");
+  }
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(gcr_smem_u32(bar)) : "memory");
+}
+__forceinline__ __device__ void gcr_cp_async_wait_all() {
+  asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
 // Vector float reduction to global memory (SASS REDG.E.ADD.F32x4); addr 16 B aligned.
 __forceinline__ __device__ void gcr_red_add_v4(float4* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(a), "f"(b), "f"(c),

@@ -27,147 +27,175 @@ __forceinline__ __device__ float xf3(const float* __restrict__ m, int k, float x
   return __fmaf_rn(z, m[8 + k], __fmaf_rn(x, m[k], __fmul_rn(y, m[4 + k])));
 }
 
-// number of tile rows r in [y0, y1) with r % count == rank
-__forceinline__ __device__ int owned_rows(int y0, int y1, int rank, int count) {
-  if (count <= 1) return y1 - y0;
-  if (y1 <= y0) return 0;
-  // rows < y with r%count==rank : (y - rank + count - 1) / count  for y >= 0
-  auto below = [&](int y) { return (y - rank + count - 1) / count; };
-  return max(0, below(y1)) - max(0, below(y0));
-}
+// Projection of one Gaussian: everything of preprocessCUDA (forward.cu:147-215) that does not
+// involve colour.  Shared by the forward kernel and the stripe-partition pre-pass.
+struct GcrProjected {
+  float vz, pix_x, pix_y, conic_x, conic_y, conic_z;
+  int radius;
+  uint2 rmin, rmax;
+};
 
-template <bool kHasSH>
-__global__ void __launch_bounds__(256, 3)   // <= 85 registers: 3 CTAs/SM for this streaming kernel
-preprocess_fwd_kernel(GcrPreprocessArgs a) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= a.P) return;
-
-  // Defaults for culled Gaussians.
-  int radius_out = 0;
-  uint32_t tiles = 0;
-  uint32_t depth_key = 0xFFFFFFFFu;  // sorts behind every visible Gaussian
-
-  const float px = a.means3D[3 * idx + 0];
-  const float py = a.means3D[3 * idx + 1];
-  const float pz = a.means3D[3 * idx + 2];
-
+__forceinline__ __device__ bool gcr_project(const GcrPreprocessArgs& a, int idx, float px, float py,
+                                            float pz, GcrProjected& o) {
   const float* __restrict__ V = a.viewmatrix;
   const float* __restrict__ PM = a.projmatrix;
 
   // in_frustum: view-space depth test (auxiliary.h:141-154)
   const float vz = __fadd_rn(xf3(V, 2, px, py, pz), V[14]);
-  bool visible = vz > 0.2f;
-  if (!visible && a.prefiltered) {
-    printf("Point is filtered although prefiltered is set. This shouldn't happen!");
-    __trap();
+  const bool visible = vz > 0.2f;
+  if (!visible) {
+    if (a.prefiltered) {
+      printf("Point is filtered although prefiltered is set. This shouldn't happen!");
+      __trap();
+    }
+    return false;
+  }
+  // clip-space projection (forward.cu:179-181)
+  const float hx = __fadd_rn(xf3(PM, 0, px, py, pz), PM[12]);
+  const float hy = __fadd_rn(xf3(PM, 1, px, py, pz), PM[13]);
+  const float hw = __fadd_rn(xf3(PM, 3, px, py, pz), PM[15]);
+  const float p_w = 1.0f / __fadd_rn(hw, 0.0000001f);
+  const float ndc_x = __fmul_rn(hx, p_w);
+  const float ndc_y = __fmul_rn(hy, p_w);
+
+  // 3D covariance (forward.cu:110-144) -- quaternion deliberately NOT normalised.
+  float c0, c1, c2, c3, c4, c5;
+  if (a.cov3D_precomp != nullptr) {
+    const float* c = a.cov3D_precomp + 6 * (size_t)idx;
+    c0 = c[0]; c1 = c[1]; c2 = c[2]; c3 = c[3]; c4 = c[4]; c5 = c[5];
+  } else {
+    const float s0 = __fmul_rn(a.scale_modifier, a.scales[3 * idx + 0]);
+    const float s1 = __fmul_rn(a.scale_modifier, a.scales[3 * idx + 1]);
+    const float s2 = __fmul_rn(a.scale_modifier, a.scales[3 * idx + 2]);
+    const float4 q = reinterpret_cast<const float4*>(a.rotations)[idx];
+    const float r = q.x, x = q.y, y = q.z, z = q.w;
+    // R columns (GLM column-major constructor order)
+    // (decoded from the reference SASS: shared products are materialised, the other one fused;
+    //  yy + zz is a plain add, xz +- ry fuses r*y onto rn(x*z))
+    const float R00 = __fsub_rn(1.f, __fmul_rn(2.f, __fadd_rn(__fmul_rn(y, y), __fmul_rn(z, z))));
+    const float R01 = __fmul_rn(2.f, __fmaf_rn(x, y, -__fmul_rn(r, z)));
+    const float R02 = __fmul_rn(2.f, __fmaf_rn(r, y, __fmul_rn(x, z)));
+    const float R10 = __fmul_rn(2.f, __fmaf_rn(x, y, __fmul_rn(r, z)));
+    const float R11 = __fsub_rn(1.f, __fmul_rn(2.f, __fmaf_rn(x, x, __fmul_rn(z, z))));
+    const float R12 = __fmul_rn(2.f, __fmaf_rn(y, z, -__fmul_rn(r, x)));
+    const float R20 = __fmul_rn(2.f, __fmaf_rn(-r, y, __fmul_rn(x, z)));
+    const float R21 = __fmul_rn(2.f, __fmaf_rn(y, z, __fmul_rn(r, x)));
+    const float R22 = __fsub_rn(1.f, __fmul_rn(2.f, __fmaf_rn(x, x, __fmul_rn(y, y))));
+    // M = S * R  ->  M[i][j] = s_j * R[i][j]   (column i, row j)
+    const float M00 = __fmul_rn(s0, R00), M01 = __fmul_rn(s1, R01), M02 = __fmul_rn(s2, R02);
+    const float M10 = __fmul_rn(s0, R10), M11 = __fmul_rn(s1, R11), M12 = __fmul_rn(s2, R12);
+    const float M20 = __fmul_rn(s0, R20), M21 = __fmul_rn(s1, R21), M22 = __fmul_rn(s2, R22);
+    // Sigma = M^T M : Sigma[i][j] = M[j][0]*M[i][0] + M[j][1]*M[i][1] + M[j][2]*M[i][2]
+    c0 = dot3(M00, M00, M01, M01, M02, M02);
+    c1 = dot3(M10, M00, M11, M01, M12, M02);
+    c2 = dot3(M20, M00, M21, M01, M22, M02);
+    c3 = dot3(M10, M10, M11, M11, M12, M12);
+    c4 = dot3(M20, M10, M21, M11, M22, M12);
+    c5 = dot3(M20, M20, M21, M21, M22, M22);
+  }
+  if (a.dbg_cov3D != nullptr) {
+    float* c = a.dbg_cov3D + 6 * (size_t)idx;
+    c[0] = c0; c[1] = c1; c[2] = c2; c[3] = c3; c[4] = c4; c[5] = c5;
   }
 
-  if (visible) {
-    // clip-space projection (forward.cu:179-181)
-    const float hx = __fadd_rn(xf3(PM, 0, px, py, pz), PM[12]);
-    const float hy = __fadd_rn(xf3(PM, 1, px, py, pz), PM[13]);
-    const float hw = __fadd_rn(xf3(PM, 3, px, py, pz), PM[15]);
-    const float p_w = 1.0f / __fadd_rn(hw, 0.0000001f);
-    const float ndc_x = __fmul_rn(hx, p_w);
-    const float ndc_y = __fmul_rn(hy, p_w);
+  // 2D covariance (forward.cu:69-105), EWA splatting with clamped view-space x/z, y/z.
+  float tx = __fadd_rn(xf3(V, 0, px, py, pz), V[12]);
+  float ty = __fadd_rn(xf3(V, 1, px, py, pz), V[13]);
+  const float tz = vz;
+  const float limx = __fmul_rn(1.3f, a.tan_fovx);
+  const float limy = __fmul_rn(1.3f, a.tan_fovy);
+  const float txtz = tx / tz;
+  const float tytz = ty / tz;
+  tx = __fmul_rn(fminf(limx, fmaxf(-limx, txtz)), tz);
+  ty = __fmul_rn(fminf(limy, fmaxf(-limy, tytz)), tz);
+  const float tz2 = __fmul_rn(tz, tz);
+  const float J00 = a.focal_x / tz;
+  const float J02 = -__fmul_rn(a.focal_x, tx) / tz2;
+  const float J11 = a.focal_y / tz;
+  const float J12 = -__fmul_rn(a.focal_y, ty) / tz2;
+  // T = W * J with W[k][j] = V[4*j + k]; T[0][j] = fma(W2j,J02, rn(W0j*J00)),
+  // T[1][j] = fma(W2j,J12, rn(W1j*J11)), T[2][j] = 0.
+  const float T00 = __fmaf_rn(V[2], J02, __fmul_rn(V[0], J00));
+  const float T01 = __fmaf_rn(V[6], J02, __fmul_rn(V[4], J00));
+  const float T02 = __fmaf_rn(V[10], J02, __fmul_rn(V[8], J00));
+  const float T10 = __fmaf_rn(V[2], J12, __fmul_rn(V[1], J11));
+  const float T11 = __fmaf_rn(V[6], J12, __fmul_rn(V[5], J11));
+  const float T12 = __fmaf_rn(V[10], J12, __fmul_rn(V[9], J11));
+  // X = T^T * Vrk^T : X[i][j] = T[j][0]*S(i,0) + T[j][1]*S(i,1) + T[j][2]*S(i,2)
+  const float X00 = dot3(T00, c0, T01, c1, T02, c2);
+  const float X10 = dot3(T00, c1, T01, c3, T02, c4);
+  const float X20 = dot3(T00, c2, T01, c4, T02, c5);
+  const float X01 = dot3(T10, c0, T11, c1, T12, c2);
+  const float X11 = dot3(T10, c1, T11, c3, T12, c4);
+  const float X21 = dot3(T10, c2, T11, c4, T12, c5);
+  // cov = X * T : cov[i][j] = X[0][j]*T[i][0] + X[1][j]*T[i][1] + X[2][j]*T[i][2]
+  float cov_x = dot3(X00, T00, X10, T01, X20, T02);
+  const float cov_y = dot3(X01, T00, X11, T01, X21, T02);
+  float cov_z = dot3(X01, T10, X11, T11, X21, T12);
+  cov_x = __fadd_rn(cov_x, 0.3f);
+  cov_z = __fadd_rn(cov_z, 0.3f);
 
-    // 3D covariance (forward.cu:110-144) -- quaternion deliberately NOT normalised.
-    float c0, c1, c2, c3, c4, c5;
-    if (a.cov3D_precomp != nullptr) {
-      const float* c = a.cov3D_precomp + 6 * (size_t)idx;
-      c0 = c[0]; c1 = c[1]; c2 = c[2]; c3 = c[3]; c4 = c[4]; c5 = c[5];
-    } else {
-      const float s0 = __fmul_rn(a.scale_modifier, a.scales[3 * idx + 0]);
-      const float s1 = __fmul_rn(a.scale_modifier, a.scales[3 * idx + 1]);
-      const float s2 = __fmul_rn(a.scale_modifier, a.scales[3 * idx + 2]);
-      const float4 q = reinterpret_cast<const float4*>(a.rotations)[idx];
-      const float r = q.x, x = q.y, y = q.z, z = q.w;
-      // R columns (GLM column-major constructor order)
-      // (decoded from the reference SASS: shared products are materialised, the other one fused;
-      //  yy + zz is a plain add, xz +- ry fuses r*y onto rn(x*z))
-      const float R00 = __fsub_rn(1.f, __fmul_rn(2.f, __fadd_rn(__fmul_rn(y, y), __fmul_rn(z, z))));
-      const float R01 = __fmul_rn(2.f, __fmaf_rn(x, y, -__fmul_rn(r, z)));
-      const float R02 = __fmul_rn(2.f, __fmaf_rn(r, y, __fmul_rn(x, z)));
-      const float R10 = __fmul_rn(2.f, __fmaf_rn(x, y, __fmul_rn(r, z)));
-      const float R11 = __fsub_rn(1.f, __fmul_rn(2.f, __fmaf_rn(x, x, __fmul_rn(z, z))));
-      const float R12 = __fmul_rn(2.f, __fmaf_rn(y, z, -__fmul_rn(r, x)));
-      const float R20 = __fmul_rn(2.f, __fmaf_rn(-r, y, __fmul_rn(x, z)));
-      const float R21 = __fmul_rn(2.f, __fmaf_rn(y, z, __fmul_rn(r, x)));
-      const float R22 = __fsub_rn(1.f, __fmul_rn(2.f, __fmaf_rn(x, x, __fmul_rn(y, y))));
-      // M = S * R  ->  M[i][j] = s_j * R[i][j]   (column i, row j)
-      const float M00 = __fmul_rn(s0, R00), M01 = __fmul_rn(s1, R01), M02 = __fmul_rn(s2, R02);
-      const float M10 = __fmul_rn(s0, R10), M11 = __fmul_rn(s1, R11), M12 = __fmul_rn(s2, R12);
-      const float M20 = __fmul_rn(s0, R20), M21 = __fmul_rn(s1, R21), M22 = __fmul_rn(s2, R22);
-      // Sigma = M^T M : Sigma[i][j] = M[j][0]*M[i][0] + M[j][1]*M[i][1] + M[j][2]*M[i][2]
-      c0 = dot3(M00, M00, M01, M01, M02, M02);
-      c1 = dot3(M10, M00, M11, M01, M12, M02);
-      c2 = dot3(M20, M00, M21, M01, M22, M02);
-      c3 = dot3(M10, M10, M11, M11, M12, M12);
-      c4 = dot3(M20, M10, M21, M11, M22, M12);
-      c5 = dot3(M20, M20, M21, M21, M22, M22);
+  // conic = inverse (forward.cu:196-201)
+  const float det = __fmaf_rn(cov_x, cov_z, -__fmul_rn(cov_y, cov_y));
+  if (det == 0.0f) return false;
+  const float det_inv = 1.f / det;
+  o.conic_x = __fmul_rn(cov_z, det_inv);
+  o.conic_y = __fmul_rn(cov_y, -det_inv);
+  o.conic_z = __fmul_rn(cov_x, det_inv);
+
+  // screen-space extent (forward.cu:203-215)
+  const float mid = __fmul_rn(0.5f, __fadd_rn(cov_x, cov_z));
+  const float sq = sqrtf(fmaxf(0.1f, __fmaf_rn(mid, mid, -det)));
+  const float lambda1 = __fadd_rn(mid, sq);
+  const float lambda2 = __fsub_rn(mid, sq);
+  const float my_radius = ceilf(__fmul_rn(3.f, sqrtf(fmaxf(lambda1, lambda2))));
+  o.pix_x = gcr_ndc2pix(ndc_x, a.W);
+  o.pix_y = gcr_ndc2pix(ndc_y, a.H);
+  o.radius = (int)my_radius;
+  o.vz = vz;
+  gcr_get_rect(o.pix_x, o.pix_y, o.radius, a.grid_x, a.grid_y, o.rmin, o.rmax);
+  return (o.rmax.x - o.rmin.x) * (o.rmax.y - o.rmin.y) != 0;
+}
+
+// rank whose stripe [bounds[r], bounds[r+1]) holds the Gaussian's centre tile row, clamped into
+// the rows its rect touches (the centre row always is one of them: radius >= 1)
+__forceinline__ __device__ int gcr_owner_rank(const GcrPreprocessArgs& a, const GcrProjected& g) {
+  if (a.stripe_bounds == nullptr) return 0;
+  int cr = (int)floorf(g.pix_y * (1.0f / GCR_TILE_Y));
+  cr = min(max(cr, (int)g.rmin.y), (int)g.rmax.y - 1);
+  int owner = 0;
+  for (int r = 1; r < a.shard_count; ++r)
+    if (cr >= a.stripe_bounds[r]) owner = r;
+  return owner;
+}
+
+template <bool kHasSH>
+__forceinline__ __device__ uint32_t preprocess_one(const GcrPreprocessArgs& a, const int idx) {
+  // Defaults for culled Gaussians.
+  int radius_out = 0;
+  uint32_t tiles = 0;
+  uint32_t depth_key = 0xFFFFFFFFu;  // dropped by the first pass of the depth sort
+  uint8_t owner_out = GCR_NO_OWNER;
+
+  const float px = a.means3D[3 * idx + 0];
+  const float py = a.means3D[3 * idx + 1];
+  const float pz = a.means3D[3 * idx + 2];
+
+  GcrProjected g;
+  if (gcr_project(a, idx, px, py, pz, g)) {
+    radius_out = g.radius;
+    const int owner = gcr_owner_rank(a, g);
+    owner_out = (uint8_t)owner;
+    // rows of the rect inside this rank's stripe (all of them without sharding)
+    int row0 = 0, row1 = a.grid_y;
+    if (a.stripe_bounds != nullptr) {
+      row0 = a.stripe_bounds[a.shard_rank];
+      row1 = a.stripe_bounds[a.shard_rank + 1];
     }
-    if (a.dbg_cov3D != nullptr) {
-      float* c = a.dbg_cov3D + 6 * (size_t)idx;
-      c[0] = c0; c[1] = c1; c[2] = c2; c[3] = c3; c[4] = c4; c[5] = c5;
-    }
-
-    // 2D covariance (forward.cu:69-105), EWA splatting with clamped view-space x/z, y/z.
-    float tx = __fadd_rn(xf3(V, 0, px, py, pz), V[12]);
-    float ty = __fadd_rn(xf3(V, 1, px, py, pz), V[13]);
-    const float tz = vz;
-    const float limx = __fmul_rn(1.3f, a.tan_fovx);
-    const float limy = __fmul_rn(1.3f, a.tan_fovy);
-    const float txtz = tx / tz;
-    const float tytz = ty / tz;
-    tx = __fmul_rn(fminf(limx, fmaxf(-limx, txtz)), tz);
-    ty = __fmul_rn(fminf(limy, fmaxf(-limy, tytz)), tz);
-    const float tz2 = __fmul_rn(tz, tz);
-    const float J00 = a.focal_x / tz;
-    const float J02 = -__fmul_rn(a.focal_x, tx) / tz2;
-    const float J11 = a.focal_y / tz;
-    const float J12 = -__fmul_rn(a.focal_y, ty) / tz2;
-    // T = W * J with W[k][j] = V[4*j + k]; T[0][j] = fma(W2j,J02, rn(W0j*J00)),
-    // T[1][j] = fma(W2j,J12, rn(W1j*J11)), T[2][j] = 0.
-    const float T00 = __fmaf_rn(V[2], J02, __fmul_rn(V[0], J00));
-    const float T01 = __fmaf_rn(V[6], J02, __fmul_rn(V[4], J00));
-    const float T02 = __fmaf_rn(V[10], J02, __fmul_rn(V[8], J00));
-    const float T10 = __fmaf_rn(V[2], J12, __fmul_rn(V[1], J11));
-    const float T11 = __fmaf_rn(V[6], J12, __fmul_rn(V[5], J11));
-    const float T12 = __fmaf_rn(V[10], J12, __fmul_rn(V[9], J11));
-    // X = T^T * Vrk^T : X[i][j] = T[j][0]*S(i,0) + T[j][1]*S(i,1) + T[j][2]*S(i,2)
-    const float X00 = dot3(T00, c0, T01, c1, T02, c2);
-    const float X10 = dot3(T00, c1, T01, c3, T02, c4);
-    const float X20 = dot3(T00, c2, T01, c4, T02, c5);
-    const float X01 = dot3(T10, c0, T11, c1, T12, c2);
-    const float X11 = dot3(T10, c1, T11, c3, T12, c4);
-    const float X21 = dot3(T10, c2, T11, c4, T12, c5);
-    // cov = X * T : cov[i][j] = X[0][j]*T[i][0] + X[1][j]*T[i][1] + X[2][j]*T[i][2]
-    float cov_x = dot3(X00, T00, X10, T01, X20, T02);
-    const float cov_y = dot3(X01, T00, X11, T01, X21, T02);
-    float cov_z = dot3(X01, T10, X11, T11, X21, T12);
-    cov_x = __fadd_rn(cov_x, 0.3f);
-    cov_z = __fadd_rn(cov_z, 0.3f);
-
-    // conic = inverse (forward.cu:196-201)
-    const float det = __fmaf_rn(cov_x, cov_z, -__fmul_rn(cov_y, cov_y));
-    if (det != 0.0f) {
-      const float det_inv = 1.f / det;
-      const float conic_x = __fmul_rn(cov_z, det_inv);
-      const float conic_y = __fmul_rn(cov_y, -det_inv);
-      const float conic_z = __fmul_rn(cov_x, det_inv);
-
-      // screen-space extent (forward.cu:203-215)
-      const float mid = __fmul_rn(0.5f, __fadd_rn(cov_x, cov_z));
-      const float sq = sqrtf(fmaxf(0.1f, __fmaf_rn(mid, mid, -det)));
-      const float lambda1 = __fadd_rn(mid, sq);
-      const float lambda2 = __fsub_rn(mid, sq);
-      const float my_radius = ceilf(__fmul_rn(3.f, sqrtf(fmaxf(lambda1, lambda2))));
-      const float pix_x = gcr_ndc2pix(ndc_x, a.W);
-      const float pix_y = gcr_ndc2pix(ndc_y, a.H);
-      uint2 rmin, rmax;
-      gcr_get_rect(pix_x, pix_y, (int)my_radius, a.grid_x, a.grid_y, rmin, rmax);
-      const uint32_t touched = (rmax.x - rmin.x) * (rmax.y - rmin.y);
-      if (touched != 0) {
+    const int y0 = max((int)g.rmin.y, row0), y1 = min((int)g.rmax.y, row1);
+    if (y1 > y0) {
+      tiles = (g.rmax.x - g.rmin.x) * (uint32_t)(y1 - y0);
+      {
         // colour: SH evaluation (forward.cu:20-66) or precomputed
         float cr, cg, cb;
         if (kHasSH) {
@@ -282,24 +310,93 @@ preprocess_fwd_kernel(GcrPreprocessArgs a) {
 
         const float opacity = a.opacities[idx];
         GcrRecord rec;
-        rec.q0 = make_float4(pix_x, pix_y, conic_x, conic_y);
-        rec.q1 = make_float4(conic_z, opacity, cr, cg);
+        rec.q0 = make_float4(g.pix_x, g.pix_y, g.conic_x, g.conic_y);
+        rec.q1 = make_float4(g.conic_z, opacity, cr, cg);
         // cull threshold 2*ln(255*opacity): a pixel can only reach alpha >= 1/255 when
         // A dx^2 + 2B dx dy + C dy^2 <= this value (used with a safety margin, blend_*.cu).
-        rec.q2 = make_float4(cb, __uint_as_float((uint32_t)idx), 2.0f * logf(255.0f * opacity), 0.f);
+        rec.q2 = make_float4(cb, __uint_as_float((uint32_t)idx), 2.0f * logf(255.0f * opacity),
+                             __uint_as_float((uint32_t)owner));
         a.records[idx] = rec;
-
-        radius_out = (int)my_radius;
-        depth_key = __float_as_uint(vz);
-        // tile count restricted to the tile rows this rank owns (all rows when count == 1)
-        tiles = (rmax.x - rmin.x) *
-                (uint32_t)owned_rows((int)rmin.y, (int)rmax.y, a.shard_rank, a.shard_count);
+        depth_key = __float_as_uint(g.vz);
       }
     }
   }
   a.radii[idx] = radius_out;
   a.tiles_touched[idx] = tiles;
   a.depth_keys[idx] = depth_key;
+  a.owner[idx] = owner_out;
+  return tiles;
+}
+
+template <bool kHasSH>
+__global__ void __launch_bounds__(256, 3)   // <= 85 registers: 3 CTAs/SM for this streaming kernel
+preprocess_fwd_kernel(GcrPreprocessArgs a) {
+  __shared__ uint32_t s_sum;
+  if (threadIdx.x == 0) s_sum = 0;
+  __syncthreads();
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t tiles = 0;
+  if (idx < a.P) tiles = preprocess_one<kHasSH>(a, idx);
+  // num_rendered = sum of the tile counts: one reduction per CTA, so the host can size the
+  // binning buffer while the depth sort is still running (api.cu)
+  const uint32_t wsum = __reduce_add_sync(0xffffffffu, tiles);
+  if ((threadIdx.x & 31) == 0 && wsum != 0) atomicAdd(&s_sum, wsum);
+  __syncthreads();
+  if (threadIdx.x == 0 && s_sum != 0) atomicAdd(a.total_tiles, (unsigned long long)s_sum);
+}
+
+// Stripe partition pre-pass: per tile row, the number of tile instances (rect width summed over
+// the Gaussians whose rect covers the row); the last CTA to finish cuts the rows into
+// shard_count contiguous stripes of about equal instance count.
+constexpr int kPartRowsSmem = 1024;
+__global__ void __launch_bounds__(256)
+stripe_partition_kernel(GcrPreprocessArgs a, uint32_t* __restrict__ row_hist, int* __restrict__ bounds) {
+  __shared__ uint32_t hist[kPartRowsSmem];
+  __shared__ bool s_last;
+  const bool use_smem = a.grid_y <= kPartRowsSmem;
+  if (use_smem)
+    for (int r = threadIdx.x; r < a.grid_y; r += blockDim.x) hist[r] = 0;
+  __syncthreads();
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < a.P; idx += gridDim.x * blockDim.x) {
+    const float px = a.means3D[3 * idx + 0];
+    const float py = a.means3D[3 * idx + 1];
+    const float pz = a.means3D[3 * idx + 2];
+    GcrProjected g;
+    if (gcr_project(a, idx, px, py, pz, g)) {
+      const uint32_t w = g.rmax.x - g.rmin.x;
+      for (uint32_t r = g.rmin.y; r < g.rmax.y; ++r) atomicAdd(use_smem ? &hist[r] : &row_hist[r], w);
+    }
+  }
+  __syncthreads();
+  if (use_smem)
+    for (int r = threadIdx.x; r < a.grid_y; r += blockDim.x)
+      if (hist[r] != 0) atomicAdd(&row_hist[r], hist[r]);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&row_hist[a.grid_y], 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last || threadIdx.x != 0) return;
+  __threadfence();
+  volatile uint32_t* h = row_hist;
+  unsigned long long total = 0;
+  for (int r = 0; r < a.grid_y; ++r) total += h[r];
+  const int n = a.shard_count;
+  bounds[0] = 0;
+  bounds[n] = a.grid_y;
+  if (total == 0) {
+    for (int k = 1; k < n; ++k) bounds[k] = (int)((long long)a.grid_y * k / n);
+    return;
+  }
+  // bounds[k] = the row boundary whose instance prefix is nearest to k/n of the total
+  unsigned long long prefix = 0;   // instances in rows < r
+  int r = 0;
+  for (int k = 1; k < n; ++k) {
+    const unsigned long long target = total * (unsigned long long)k / (unsigned long long)n;
+    while (r < a.grid_y && prefix + h[r] <= target) prefix += h[r++];
+    // boundary at r (prefix <= target) or r + 1 (prefix + h[r] > target): take the nearer
+    if (r < a.grid_y && (prefix + h[r] - target) < (target - prefix)) prefix += h[r++];
+    bounds[k] = r;
+  }
 }
 
 // mark_visible (rasterizer_impl.cu:52-62): z_view > 0.2
@@ -314,17 +411,27 @@ __global__ void check_frustum_kernel(int P, const float* __restrict__ means3D,
 
 }  // namespace
 
-void gcr_launch_preprocess_fwd(const GcrPreprocessArgs& a, cudaStream_t stream) {
-  if (a.P <= 0) return;
+cudaError_t gcr_launch_preprocess_fwd(const GcrPreprocessArgs& a, cudaStream_t stream) {
+  if (a.P <= 0) return cudaSuccess;
   const int blocks = (a.P + 255) / 256;
   if (a.colors_precomp == nullptr)
     preprocess_fwd_kernel<true><<<blocks, 256, 0, stream>>>(a);
   else
     preprocess_fwd_kernel<false><<<blocks, 256, 0, stream>>>(a);
+  return cudaGetLastError();
 }
 
-void gcr_launch_check_frustum(int P, const float* means3D, const float* viewmatrix, bool* present,
-                              cudaStream_t stream) {
-  if (P <= 0) return;
+cudaError_t gcr_launch_stripe_partition(const GcrPreprocessArgs& a, uint32_t* row_hist, int* bounds_out,
+                                        cudaStream_t stream) {
+  if (a.P <= 0) return cudaSuccess;
+  const int blocks = (a.P + 255) / 256;
+  stripe_partition_kernel<<<blocks < 148 * 8 ? blocks : 148 * 8, 256, 0, stream>>>(a, row_hist, bounds_out);
+  return cudaGetLastError();
+}
+
+cudaError_t gcr_launch_check_frustum(int P, const float* means3D, const float* viewmatrix, bool* present,
+                                     cudaStream_t stream) {
+  if (P <= 0) return cudaSuccess;
   check_frustum_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, means3D, viewmatrix, present);
+  return cudaGetLastError();
 }

@@ -34,7 +34,9 @@ preprocess_bwd_kernel(GcrPreprocessBwdArgs a) {
   if (loc >= a.range_count) return;
   const int idx = a.range_start + loc;
 
-  const bool visible = a.radii[idx] > 0;
+  // differentiated here: the Gaussians this rank owns (on one GPU: every visible one)
+  const bool visible = a.owner[idx] == (uint8_t)a.my_rank;
+  if (!visible && !a.zero_unowned) return;   // tile-sharded: another rank (or nobody) owns it
   float o_m2x = 0.f, o_m2y = 0.f, o_op = 0.f, o_cr = 0.f, o_cg = 0.f, o_cb = 0.f;
   float o_ca = 0.f, o_cbb = 0.f, o_cc = 0.f;
   float dmean[3] = {0.f, 0.f, 0.f};
@@ -48,6 +50,10 @@ preprocess_bwd_kernel(GcrPreprocessBwdArgs a) {
     const float4 g0 = a.grad_acc[idx].g0;
     const float4 g1 = a.grad_acc[idx].g1;
     const float g2x = a.grad_acc[idx].g2.x;
+    if (a.clear_acc) {   // persistent (peer-mapped) accumulator: leave it zeroed for the next frame
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      a.grad_acc[idx].g0 = z; a.grad_acc[idx].g1 = z; a.grad_acc[idx].g2 = z;
+    }
     o_m2x = g0.x; o_m2y = g0.y; o_ca = g0.z; o_cbb = g0.w; o_cc = g1.x; o_op = g1.y;
     o_cr = g1.z; o_cg = g1.w; o_cb = g2x;
 
@@ -367,11 +373,12 @@ preprocess_bwd_kernel(GcrPreprocessBwdArgs a) {
 
 }  // namespace
 
-void gcr_launch_preprocess_bwd(const GcrPreprocessBwdArgs& a, cudaStream_t stream) {
-  if (a.P <= 0 || a.range_count <= 0) return;
+cudaError_t gcr_launch_preprocess_bwd(const GcrPreprocessBwdArgs& a, cudaStream_t stream) {
+  if (a.P <= 0 || a.range_count <= 0) return cudaSuccess;
   const int blocks = (a.range_count + 255) / 256;
   if (a.shs != nullptr && a.M > 0)
     preprocess_bwd_kernel<true><<<blocks, 256, 0, stream>>>(a);
   else
     preprocess_bwd_kernel<false><<<blocks, 256, 0, stream>>>(a);
+  return cudaGetLastError();
 }

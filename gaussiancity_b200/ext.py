@@ -71,8 +71,12 @@ class _Allocator:
 def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier,
                         cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height,
                         image_width, sh, degree, campos, prefiltered, debug,
-                        shard_rank=0, shard_count=1):
-    """-> (num_rendered, color[3,H,W], radii[P] int32, geomBuffer, binningBuffer, imgBuffer)"""
+                        shard_rank=0, shard_count=1, stripe_bounds=None):
+    """-> (num_rendered, color[3,H,W], radii[P] int32, geomBuffer, binningBuffer, imgBuffer)
+
+    shard_count > 1 renders one contiguous tile-row stripe of the frame (the rest of `color` is
+    zero); stripe_bounds: int32 CUDA tensor [shard_count + 1] (e.g. from stripe_partition), None
+    = equal-height stripes."""
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")
     if not means3D.is_cuda:
@@ -102,14 +106,19 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
             projmatrix = _prep(projmatrix, "projmatrix", device)
             sh = _prep(sh, "sh", device, align=32)
             campos = _prep(campos, "campos", device)
-            rc = lib.gcr_rasterizer_forward(
+            if stripe_bounds is not None:
+                if (stripe_bounds.dtype != torch.int32 or stripe_bounds.device != device or
+                        stripe_bounds.numel() != int(shard_count) + 1):
+                    raise RuntimeError("stripe_bounds must be an int32 tensor [shard_count + 1] on the device")
+                stripe_bounds = stripe_bounds.contiguous()
+            rc = lib.gcr_rasterizer_forward_striped(
                 geom.cb, None, binning.cb, None, img.cb, None,
                 P, int(degree), M, _ptr(background), W, H,
                 _ptr(means3D), _ptr(sh), _ptr(colors), _ptr(opacity), _ptr(scales),
                 float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp), _ptr(viewmatrix),
                 _ptr(projmatrix), _ptr(campos), float(tan_fovx), float(tan_fovy),
                 int(bool(prefiltered)), _ptr(out_color), _ptr(radii), int(bool(debug)),
-                int(shard_rank), int(shard_count), _stream_ptr(device))
+                int(shard_rank), int(shard_count), _ptr(stripe_bounds), _stream_ptr(device))
             rendered = _cabi.check(rc, "rasterize_gaussians")
     return rendered, out_color, radii, geom.take(), binning.take(), img.take()
 
@@ -117,9 +126,10 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
 def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations,
                                  scale_modifier, cov3D_precomp, viewmatrix, projmatrix, tan_fovx,
                                  tan_fovy, dL_dout_color, sh, degree, campos, geomBuffer, R,
-                                 binningBuffer, imageBuffer, debug, shard_rank=0, shard_count=1):
+                                 binningBuffer, imageBuffer, debug):
     """-> (dL_dmeans2D[P,3], dL_dcolors[P,3], dL_dopacity[P,1], dL_dmeans3D[P,3],
-           dL_dcov3D[P,6], dL_dsh[P,M,3], dL_dscales[P,3], dL_drotations[P,4])"""
+           dL_dcov3D[P,6], dL_dsh[P,M,3], dL_dscales[P,3], dL_drotations[P,4])
+    (a striped frame goes through rasterize_gaussians_backward_blend / _geometry)"""
     lib = _cabi.lib()
     device = means3D.device
     P = int(means3D.size(0))
@@ -160,7 +170,7 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
                 _ptr(dL_dout_color), _ptr(dL_dmeans2D), None, _ptr(dL_dopacity),
                 _ptr(dL_dcolors), _ptr(dL_dmeans3D), _ptr(dL_dcov3D), _ptr(dL_dsh),
                 _ptr(dL_dscales), _ptr(dL_drotations), int(bool(debug)),
-                int(shard_rank), int(shard_count), _stream_ptr(device))
+                0, 1, _stream_ptr(device))
             _cabi.check(rc, "rasterize_gaussians_backward")
     return (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales,
             dL_drotations)
@@ -186,25 +196,70 @@ def mark_visible(means3D, viewmatrix, projmatrix):
     return present
 
 
-# ---- split backward for tile-sharded multi-GPU rendering (gaussiancity_b200.sharding) --------
-def rasterize_gaussians_backward_blend(background, P, R, dL_dout_color, binningBuffer, imageBuffer,
-                                       debug=False, shard_rank=0, shard_count=1):
-    """First half of the backward: per-tile gradient blend over this rank's tile rows.
-    -> grad_acc [P,12] fp32 (dmean2D.xy, dconic.xyw, dopacity, dcolor.rgb, 3 pad): PARTIAL sums
-    when shard_count > 1 (reduce across ranks before the geometry half)."""
+# ---- tile-row stripes of a multi-GPU frame (gaussiancity_b200.sharding) -------------------------
+def stripe_partition(means3D, scales, rotations, scale_modifier, viewmatrix, projmatrix, tan_fovx,
+                     tan_fovy, image_height, image_width, shard_count, workspace, bounds_out,
+                     cov3D_precomp=None):
+    """Balanced contiguous tile-row stripes -> bounds_out (int32 [shard_count + 1], device), no
+    host synchronisation.  workspace: int32 [ceil(H/16) + 1], device."""
+    lib = _cabi.lib()
+    device = means3D.device
+    P = int(means3D.size(0))
+    e = torch.Tensor([])
+    with torch.cuda.device(device):
+        means3D = _prep(means3D, "means3D", device)
+        scales = _prep(scales if scales is not None else e, "scales", device)
+        rotations = _prep(rotations if rotations is not None else e, "rotations", device, align=16)
+        cov3D_precomp = _prep(cov3D_precomp if cov3D_precomp is not None else e, "cov3D_precomp", device)
+        viewmatrix = _prep(viewmatrix, "viewmatrix", device)
+        projmatrix = _prep(projmatrix, "projmatrix", device)
+        rc = lib.gcr_stripe_partition(P, _ptr(means3D), _ptr(scales), float(scale_modifier), _ptr(rotations),
+                                      _ptr(cov3D_precomp), _ptr(viewmatrix), _ptr(projmatrix),
+                                      int(image_width), int(image_height), float(tan_fovx), float(tan_fovy),
+                                      int(shard_count), _ptr(workspace), _ptr(bounds_out), _stream_ptr(device))
+        _cabi.check(rc, "stripe_partition")
+    return bounds_out
+
+
+def owner_bytes(geomBuffer, P):
+    """uint8 [P]: rank that owns each Gaussian of the last forward into geomBuffer (255 = culled)."""
+    lib = _cabi.lib()
+    off = lib.gcr_debug_offset(_cabi.GEOM_OWNER, int(P), 0, 16, 16)
+    base = (-geomBuffer.data_ptr()) % 256   # the library carves from the 256-byte aligned address
+    return geomBuffer[base + off:base + off + int(P)]
+
+
+def rasterize_gaussians_backward_blend(background, P, R, dL_dout_color, geomBuffer, binningBuffer,
+                                       imageBuffer, debug=False, shard_rank=0, shard_count=1,
+                                       accumulators=None, remote_scalar=False):
+    """First half of the backward: per-tile gradient blend over this rank's stripe.
+
+    accumulators=None -> returns a fresh grad_acc [P,12] fp32 (dmean2D.xy, dconic.xyw, dopacity,
+    dcolor.rgb, 3 pad): PARTIAL sums when shard_count > 1 (reduce across ranks before the
+    geometry half).  accumulators=[device addresses, one per rank] (peer-mapped, see
+    sharding.CudaBackend.peer_setup): each Gaussian's sums are added into its owner's accumulator
+    inside the kernel; returns None."""
     lib = _cabi.lib()
     device = dL_dout_color.device
     H, W = int(dL_dout_color.size(1)), int(dL_dout_color.size(2))
     with torch.cuda.device(device):
-        grad_acc = torch.empty((int(P), 12), dtype=torch.float32, device=device)
+        grad_acc = None
+        if accumulators is None:
+            grad_acc = torch.empty((int(P), 12), dtype=torch.float32, device=device)
+            ptrs = (ctypes.c_void_p * 1)(grad_acc.data_ptr())
+            n_acc, zero_first = 1, 1
+        else:
+            ptrs = (ctypes.c_void_p * len(accumulators))(*[int(a) for a in accumulators])
+            n_acc, zero_first = len(accumulators), 0
         if P != 0:
             background = _prep(background, "background", device)
             dL_dout_color = _prep(dL_dout_color, "dL_dout_color", device)
             rc = lib.gcr_rasterizer_backward_blend(
-                int(P), int(R), _ptr(background), W, H,
+                int(P), int(R), _ptr(background), W, H, ctypes.c_void_p(geomBuffer.data_ptr()),
                 ctypes.c_void_p(binningBuffer.data_ptr()) if binningBuffer.numel() else None,
-                ctypes.c_void_p(imageBuffer.data_ptr()), _ptr(dL_dout_color), _ptr(grad_acc),
-                int(bool(debug)), int(shard_rank), int(shard_count), _stream_ptr(device))
+                ctypes.c_void_p(imageBuffer.data_ptr()), _ptr(dL_dout_color), ptrs, n_acc, zero_first,
+                int(bool(remote_scalar)), int(bool(debug)), int(shard_rank), int(shard_count),
+                _stream_ptr(device))
             _cabi.check(rc, "rasterize_gaussians_backward_blend")
     return grad_acc
 
@@ -213,11 +268,13 @@ def rasterize_gaussians_backward_geometry(means3D, radii, scales, rotations, sca
                                           cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy,
                                           image_height, image_width, sh, degree, campos, geomBuffer,
                                           grad_acc, range_start=0, range_count=-1, debug=False,
-                                          out=None):
-    """Second half of the backward: per-Gaussian geometry gradients for Gaussians
-    [range_start, range_start+range_count) from the (reduced) accumulator.  Returns the same
-    8-tuple as rasterize_gaussians_backward; rows outside the range are left untouched
-    (uninitialised unless `out` is supplied)."""
+                                          out=None, shard_rank=0, striped=False, clear_accumulator=False):
+    """Second half of the backward: per-Gaussian geometry gradients, for the Gaussians within
+    [range_start, range_start+range_count) that `shard_rank` owns, from the (reduced) accumulator
+    (a [P,12] tensor or a device address).  Returns the same 8-tuple as
+    rasterize_gaussians_backward.  striped=False: the rows of all other Gaussians in the range are
+    written as zeros; striped=True: they are left untouched (uninitialised unless `out` is
+    supplied)."""
     lib = _cabi.lib()
     device = means3D.device
     P = int(means3D.size(0))
@@ -238,13 +295,15 @@ def rasterize_gaussians_backward_geometry(means3D, radii, scales, rotations, sca
             projmatrix = _prep(projmatrix, "projmatrix", device)
             sh = _prep(sh, "sh", device, align=32)
             campos = _prep(campos, "campos", device)
+            acc_ptr = _ptr(grad_acc) if isinstance(grad_acc, torch.Tensor) else ctypes.c_void_p(int(grad_acc))
             rc = lib.gcr_rasterizer_backward_geometry(
                 P, int(degree), M, _ptr(means3D), _ptr(sh), _ptr(scales), float(scale_modifier),
                 _ptr(rotations), _ptr(cov3D_precomp), _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos),
                 int(image_width), int(image_height), float(tan_fovx), float(tan_fovy),
-                _ptr(radii.contiguous()), ctypes.c_void_p(geomBuffer.data_ptr()), _ptr(grad_acc),
+                _ptr(radii.contiguous()), ctypes.c_void_p(geomBuffer.data_ptr()), acc_ptr,
                 _ptr(dL_dmeans2D), None, _ptr(dL_dopacity), _ptr(dL_dcolors), _ptr(dL_dmeans3D),
                 _ptr(dL_dcov3D), _ptr(dL_dsh), _ptr(dL_dscales), _ptr(dL_drot), int(bool(debug)),
-                int(range_start), int(range_count), _stream_ptr(device))
+                int(range_start), int(range_count), int(shard_rank), int(bool(striped)),
+                int(bool(clear_accumulator)), _stream_ptr(device))
             _cabi.check(rc, "rasterize_gaussians_backward_geometry")
     return out

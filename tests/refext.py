@@ -94,10 +94,13 @@ def our_views(P, R, W, H, geom, binning, img):
     v["sorted_gauss"] = geom[off(C.GEOM_SORTED_GAUSS):off(C.GEOM_SORTED_GAUSS) + 4 * P].view(torch.int32)
     v["sorted_depth_keys"] = geom[off(C.GEOM_DEPTH_SORTED_KEYS):off(C.GEOM_DEPTH_SORTED_KEYS) + 4 * P].view(torch.int32)
     v["offsets"] = geom[off(C.GEOM_OFFSETS):off(C.GEOM_OFFSETS) + 4 * P].view(torch.int32)
+    v["owner"] = geom[off(C.GEOM_OWNER):off(C.GEOM_OWNER) + P]
+    # device-side counters: [0] Gaussians that reach this rank's stripe (= entries of sorted_gauss /
+    # sorted_depth_keys / offsets that are valid), [1] num_rendered, [2] overflow flag
+    v["counters"] = geom[off(C.GEOM_COUNTERS):off(C.GEOM_COUNTERS) + 12].view(torch.int32)
     if R > 0:
         v["point_list"] = binning[off(C.BIN_POINT_LIST):off(C.BIN_POINT_LIST) + 4 * R].view(torch.int32)
         v["tile_keys"] = binning[off(C.BIN_TILE_KEYS):off(C.BIN_TILE_KEYS) + 4 * R].view(torch.int32)
-        v["instances"] = binning[off(C.BIN_INSTANCES):off(C.BIN_INSTANCES) + 48 * R].view(torch.float32).view(R, 12)
     v["final_T"] = img[off(C.IMG_FINAL_T):off(C.IMG_FINAL_T) + 4 * W * H].view(torch.float32).view(H, W)
     v["n_contrib"] = img[off(C.IMG_N_CONTRIB):off(C.IMG_N_CONTRIB) + 4 * W * H].view(torch.int32).view(H, W)
     v["ranges"] = img[off(C.IMG_RANGES):off(C.IMG_RANGES) + 8 * tiles].view(torch.int32).view(tiles, 2)

@@ -37,7 +37,7 @@ def run_ours(s, grad_out=None, **kw):
     grads = None
     if grad_out is not None:
         grads = ours.rasterize_gaussians_backward(
-            *refext.scene_backward_args(s, radii, grad_out, geom, R, binning, img), **kw)
+            *refext.scene_backward_args(s, radii, grad_out, geom, R, binning, img))
     torch.cuda.synchronize()
     return out, grads
 
@@ -113,14 +113,17 @@ def test_full_size_binning_invariants(big):
     P, W, H = s.means3D.shape[0], s.img_w, s.img_h
     ov = refext.our_views(P, R, W, H, geom, binning, img)
     assert int(ov["tiles_touched"].long().sum()) == R                     # checksum of counts
-    assert int(ov["offsets"][-1]) == R
+    n_vis = int(ov["counters"][0])
+    assert n_vis == int((radii > 0).sum()) and int(ov["counters"][1]) == R and int(ov["counters"][2]) == 0
+    assert int(ov["offsets"][n_vis - 1]) == R
     keys = ov["tile_keys"].long()
     assert bool((keys[1:] >= keys[:-1]).all())                            # sorted by tile
     # within a tile: depth ascending, ties by ascending Gaussian index (stable sort semantics)
     depth = torch.full((P,), float("inf"), device=radii.device)
     vis = radii > 0
-    sg = ov["sorted_gauss"].long()
-    sk = ov["sorted_depth_keys"].view(torch.float32)
+    sg = ov["sorted_gauss"][:n_vis].long()           # culled Gaussians are dropped by the depth sort
+    sk = ov["sorted_depth_keys"][:n_vis].view(torch.float32)
+    assert bool((sk[1:] >= sk[:-1]).all()) and bool(vis[sg].all()) and sg.unique().numel() == n_vis
     depth[sg] = sk
     pl = ov["point_list"].long()
     same = keys[1:] == keys[:-1]
@@ -175,28 +178,76 @@ def test_full_size_background_enters_linearly(big, cuda_device):
     assert torch.allclose(color2, color + ft[None] * bg[:, None, None], rtol=0, atol=1e-6)
 
 
-def test_tile_row_shards_partition_the_frame(big):
-    """shard_count = 3 on one GPU, ranks run one after the other: image rows are disjoint and
-    their union is the single-GPU frame bit for bit; partial accumulators sum to the full one."""
+def _stripe_rows(bounds, k, H):
+    rows = torch.zeros(H, dtype=torch.bool)
+    rows[bounds[k] * 16:min(H, bounds[k + 1] * 16)] = True
+    return rows
+
+
+@pytest.mark.parametrize("balanced", [False, True], ids=["equal_stripes", "balanced_stripes"])
+def test_tile_row_stripes_partition_the_frame(big, balanced):
+    """shard_count = 3 on one GPU, ranks run one after the other: image stripes are disjoint and
+    their union is the single-GPU frame bit for bit; every visible Gaussian has exactly one owner
+    (the stripe of its centre row), each stripe only sorts the Gaussians that reach it, partial
+    accumulators sum to the full one, and the owners' geometry backward reproduces the monolithic
+    backward."""
+    from gaussiancity_b200 import sharding
     s, G, (R, color, radii, geom, binning, img), grads = big
-    P, H = s.means3D.shape[0], s.img_h
+    P, W, H = s.means3D.shape[0], s.img_w, s.img_h
+    dev = color.device
+    N, grid_y = 3, (H + 15) // 16
+    if balanced:
+        ws = torch.empty(grid_y + 1, dtype=torch.int32, device=dev)
+        bounds_t = torch.empty(N + 1, dtype=torch.int32, device=dev)
+        ours.stripe_partition(s.means3D, s.scales, s.rotations, 1.0, s.view_matrix, s.proj_matrix, s.tanfovx,
+                              s.tanfovy, H, W, N, ws, bounds_t)
+        bounds = bounds_t.cpu().tolist()
+        # the device partition equals its host restatement on the per-row instance histogram
+        assert int(ws[grid_y]) > 0 and int(ws[:grid_y].long().sum()) == R
+        assert bounds == sharding.balanced_stripes(ws[:grid_y].cpu().tolist(), N)
+        cnt = [int(ws[bounds[k]:bounds[k + 1]].long().sum()) for k in range(N)]
+        assert max(cnt) - min(cnt) <= 2 * int(ws[:grid_y].max())     # balanced to within ~a row
+    else:
+        bounds_t, bounds = None, sharding.equal_stripes(grid_y, N)
     total, Rsum = torch.zeros_like(color), 0
-    acc = torch.zeros(P, 12, device=color.device, dtype=torch.float64)
-    for k in range(3):
-        (Rk, ck, rk, gk, bk, ik), _ = run_ours(s, shard_rank=k, shard_count=3)
+    acc = torch.zeros(P, 12, device=dev, dtype=torch.float64)
+    owners = torch.zeros(P, dtype=torch.int32, device=dev)
+    states = []
+    for k in range(N):
+        (Rk, ck, rk, gk, bk, ik), _ = run_ours(s, shard_rank=k, shard_count=N, stripe_bounds=bounds_t)
         assert torch.equal(rk, radii)
-        rows = torch.zeros(H, dtype=torch.bool, device=color.device)
-        for r in range(k, (H + 15) // 16, 3):
-            rows[r * 16:(r + 1) * 16] = True
+        rows = _stripe_rows(bounds, k, H).to(dev)
         assert bool((ck[:, ~rows] == 0).all())
         total += ck
         Rsum += Rk
-        acc += ours.rasterize_gaussians_backward_blend(s.bg, P, Rk, G, bk, ik, shard_rank=k, shard_count=3).double()
+        ov = refext.our_views(P, Rk, W, H, gk, bk, ik)
+        own = ov["owner"]
+        assert bool(((own == 255) == (radii == 0)).all())          # culled <=> nobody owns it
+        if k == 0:
+            owner0 = own.clone()
+        assert torch.equal(own, owner0)                             # every rank agrees on the owners
+        n_vis_k = int(ov["counters"][0])
+        assert n_vis_k == int((ov["tiles_touched"] > 0).sum()) < int((radii > 0).sum())
+        assert bool((ov["tiles_touched"][own == k] > 0).all())      # an owner always reaches its Gaussians
+        owners += (own == k).int()
+        acc += ours.rasterize_gaussians_backward_blend(s.bg, P, Rk, G, gk, bk, ik, shard_rank=k, shard_count=N).double()
+        states.append((gk, rk))
     assert Rsum == R and torch.equal(total, color)
-    full = ours.rasterize_gaussians_backward_blend(s.bg, P, R, G, binning, img).double()
+    assert bool((owners == (radii > 0).int()).all())
+    full = ours.rasterize_gaussians_backward_blend(s.bg, P, R, G, geom, binning, img).double()
     assert (acc - full)[:, :9].norm().item() <= 1e-5 * full[:, :9].norm().item()
-    # finishing the geometry backward per slice reproduces the monolithic backward
+    # owners finish the geometry backward: each writes only its own rows of the shared outputs
     e = torch.Tensor([])
+    out = tuple(torch.zeros_like(g) for g in grads)
+    for k in range(N):
+        gk, rk = states[k]
+        out = ours.rasterize_gaussians_backward_geometry(
+            s.means3D, rk, s.scales, s.rotations, 1.0, e, s.view_matrix, s.proj_matrix, s.tanfovx,
+            s.tanfovy, s.img_h, s.img_w, s.shs, s.sh_degree, s.campos, gk, acc.float(),
+            out=out, shard_rank=k, striped=True)
+    for a, b in zip(out, grads):
+        assert (a.double() - b.double()).norm().item() <= 1e-5 * max(b.double().norm().item(), 1e-30)
+    # and the per-slice form on one stripe (range_start / range_count) still reproduces it
     out = None
     third = (P + 2) // 3
     for k in range(3):

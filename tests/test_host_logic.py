@@ -106,9 +106,9 @@ def test_compat_module_exports_reference_names(built_lib):
 
 def test_bench_kernel_count_formula():
     import bench
-    # 1080p: 8160 tiles -> 13 bits -> 2 tile passes; 1 + 5 + 3 + 1 + 3 + 1 + 1 (+2 backward)
+    # 1080p: 8160 tiles -> 13 bits -> 2 tile passes; 1 + 5 + 1 + 2 + 1 + 1 (+2 backward)
     assert bench.tile_sort_passes(1920, 1080) == 2
-    assert bench.kernels_per_step(1920, 1080) == 17
+    assert bench.kernels_per_step(1920, 1080) == 13
     assert bench.tile_sort_passes(128, 128) == 1
 
 

@@ -12,7 +12,12 @@ for (P, W, H, deg, use_sh, sig) in [(3000, 96, 80, 3, True, (0.5, 4.0)), (1500, 
     R, color, radii, geom, binning, img = ext.rasterize_gaussians(*refext.scene_forward_args(s))
     G = torch.ones(3, H, W, device=dev)
     grads = ext.rasterize_gaussians_backward(*refext.scene_backward_args(s, radii, G, geom, R, binning, img))
-    for k in range(2):   # sharded variant too
-        ext.rasterize_gaussians(*refext.scene_forward_args(s), shard_rank=k, shard_count=2)
+    for k in range(2):   # striped variant too: forward + both backward halves
+        Rk, ck, rk, gk, bk, ik = ext.rasterize_gaussians(*refext.scene_forward_args(s), shard_rank=k, shard_count=2)
+        acc = ext.rasterize_gaussians_backward_blend(s.bg, P, Rk, G, gk, bk, ik, shard_rank=k, shard_count=2)
+        e = torch.Tensor([])
+        ext.rasterize_gaussians_backward_geometry(s.means3D, rk, s.scales, s.rotations, 1.0, e, s.view_matrix,
+            s.proj_matrix, s.tanfovx, s.tanfovy, H, W, s.shs if s.shs is not None else e, s.sh_degree, s.campos,
+            gk, acc, shard_rank=k, striped=True)
     torch.cuda.synchronize()
     print("ok", P, W, H, "R", R, float(color.sum()), float(grads[3].abs().sum()))
