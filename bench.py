@@ -179,6 +179,145 @@ def max_over_ranks(x, device, world):
 
 
 # ------------------------------------------------------------------------------------------
+def _relerr(a, b):
+    den = b.double().norm().item()
+    return (a.double() - b.double()).norm().item() / (den if den > 0 else 1.0)
+
+
+def run_sharded_arm(args, s, inp, grad_out, rank, world, device, barrier):
+    """N > 1: ONE frame split into `world` contiguous, balanced tile-row stripes
+    (gaussiancity_b200/sharding.py).  Before anything is timed, the sharded frame and gradients are
+    checked once against this rank's own single-GPU render of the same scene."""
+    from gaussiancity_b200 import _cabi, ext, sharding
+    P, W, H = s.means3D.shape[0], s.img_w, s.img_h
+    eng = sharding.TileShardedRasterizer(device=device, exchange=args.exchange, balanced=not args.equal_stripes,
+                                         remote_scalar=args.remote_scalar)
+    cam = eng._cam(s, inp)
+    M = inp["sh"].shape[1] if inp["sh"].numel() else 0
+    opts = dict(dtype=torch.float32, device=device)
+    out = (torch.empty((P, 3), **opts), torch.empty((P, 3), **opts), torch.empty((P, 1), **opts),
+           torch.empty((P, 3), **opts), torch.empty((P, 6), **opts), torch.empty((P, M, 3), **opts),
+           torch.empty((P, 3), **opts), torch.empty((P, 4), **opts))
+
+    # ---- correctness gate (untimed): bit-identical frame, gradients <= 1e-4 --------------------
+    check = {}
+    if not args.no_check:
+        R1, col1, radii1, g1, b1, i1 = ext.rasterize_gaussians(*fwd_args(s, inp))
+        grads1 = ext.rasterize_gaussians_backward(*bwd_args(s, inp, radii1, grad_out, g1, R1, b1, i1))
+        color, radii, state = eng.render(inp, cam, assemble=True)
+        grads, owner_mask = eng.backward(state, inp, cam, grad_out)
+        full = eng.gather_gradients(grads, owner_mask)
+        Rtot = eng.num_rendered_total()
+        torch.cuda.synchronize()
+        frame_ok = bool(torch.equal(color, col1)) and bool(torch.equal(radii, radii1)) and Rtot == R1
+        errs = {n: _relerr(a, b) for n, a, b in zip(sharding.GRAD_NAMES, full, grads1) if b.numel()}
+        ok = frame_ok and all(e <= 1e-4 for e in errs.values())
+        flag = torch.tensor([1 if ok else 0], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        check = {"frame_bit_identical": frame_ok, "num_rendered_total": Rtot, "max_grad_relerr": max(errs.values()),
+                 "all_ranks_ok": bool(flag.item())}
+        if not bool(flag.item()):
+            raise SystemExit(f"[bench] rank {rank}: sharded frame != single-GPU frame: {check} {errs}")
+        del grads1, full, g1, b1, i1, col1
+    else:
+        eng.render(inp, cam, assemble=False)
+    R_total = eng.num_rendered_total()
+    R_local = eng.last_num_rendered_local
+
+    big = ("means3D", "opacity", "scales", "rotations", "sh", "colors")
+    if args.shard_mode == "broadcast":
+        # rank 0 owns the Gaussians and NCCL-broadcasts all buffers every frame, prefetched one frame
+        # ahead on a side stream into the other of two buffer sets
+        sets = [inp, {k: (v.clone() if k in big and v.numel() else v) for k, v in inp.items()}]
+        st = {"i": 0, "h": None}
+
+        def step():
+            i = st["i"]
+            if st["h"] is None and i == 0:
+                st["h"] = eng.start_prefetch({k: sets[0][k] for k in big}, src=0)
+            eng.wait_prefetch(st["h"])
+            nxt = eng.start_prefetch({k: sets[(i + 1) % 2][k] for k in big}, src=0)
+            o = eng.forward_backward(s, sets[i % 2], grad_out, assemble=args.assemble, out=out)
+            st["i"], st["h"] = i + 1, nxt
+            return o
+    else:
+        def step():
+            return eng.forward_backward(s, inp, grad_out, assemble=args.assemble, out=out)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    _cabi.profile_enable(True)
+    ms = max_over_ranks(time_steps(step, args.steps, 0, barrier), device, world)
+    stages = _cabi.profile_read()
+    _cabi.profile_enable(False)
+    fwd_only = lambda: eng.render(inp, cam, assemble=args.assemble)
+    ms_fwd = max_over_ranks(time_steps(fwd_only, max(2, args.steps // 2), 2, barrier), device, world)
+    # the other assembly mode, for the record
+    alt = lambda: eng.forward_backward(s, inp, grad_out, assemble=not args.assemble, out=out)
+    ms_alt = max_over_ranks(time_steps(alt, max(2, args.steps // 2), 2, barrier), device, world)
+    # slowest rank's stage times (max over ranks per stage): what bounds the frame
+    if stages:
+        names = sorted(stages)
+        t = torch.tensor([stages[n] for n in names], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        stages = {n: float(v) for n, v in zip(names, t.tolist())}
+    rl = torch.tensor([float(R_local)], dtype=torch.float64, device=device)
+    rmax = rl.clone()
+    dist.all_reduce(rmax, op=dist.ReduceOp.MAX)
+
+    # ---- e2e at N GPUs: every rank uploads 1/N of each input over ITS OWN PCIe link, the slices are
+    # all-gathered over NVLink, the frame is rendered / differentiated in stripes, every rank reads
+    # its own image stripe and its part of the loss back ----------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        big_keys = [k for k in big if inp[k].numel()]
+        per = (P + world - 1) // world
+        lo, hi = min(P, rank * per), min(P, (rank + 1) * per)
+        host = {k: inp[k][lo:hi].cpu().pin_memory() for k in big_keys}
+        slab = {k: torch.zeros((per,) + tuple(inp[k].shape[1:]), **opts) for k in big_keys}
+        gathered = {k: torch.empty((per * world,) + tuple(inp[k].shape[1:]), **opts) for k in big_keys}
+        bounds_h = eng.stripes(inp, cam)
+        bounds_h = bounds_h.cpu().tolist() if bounds_h is not None else sharding.equal_stripes((H + 15) // 16, world)
+        r0, r1 = bounds_h[rank] * 16, min(H, bounds_h[rank + 1] * 16)
+        host_img = torch.empty(3, max(1, r1 - r0), W, dtype=torch.float32).pin_memory()
+        host_loss = torch.empty(1, dtype=torch.float32).pin_memory()
+
+        def step_e2e():
+            for k in big_keys:
+                slab[k][:hi - lo].copy_(host[k], non_blocking=True)
+                dist.all_gather_into_tensor(gathered[k], slab[k])
+            frame = dict(inp)
+            for k in big_keys:
+                frame[k] = gathered[k][:P]
+            color, grads, state = eng.forward_backward(s, frame, grad_out, assemble=False, out=out)
+            if r1 > r0:
+                host_img[:, :r1 - r0].copy_(color[:, r0:r1], non_blocking=True)
+                host_loss.copy_((color[:, r0:r1] * grad_out[:, r0:r1]).sum().reshape(1), non_blocking=True)
+        ms_e = max_over_ranks(time_steps(step_e2e, max(2, args.steps // 2), 2, barrier), device, world)
+        h2d = sum(host[k].numel() * 4 for k in big_keys)
+        e2e = {"value": P / (ms_e * 1e-3) / 1e6, "unit": "Msplats/s", "ms_per_step": ms_e,
+               "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(3 * H * W * 4 + 4 * world),
+               "note": f"every rank uploads 1/{world} of each input from pinned host memory over its own PCIe "
+                       f"link, all_gather over NVLink, striped fwd+bwd, every rank reads its image stripe + "
+                       f"partial loss back (bytes are whole-job totals)"}
+    eng.close()
+    mode = ("Gaussians resident on every rank" if args.shard_mode == "replicated" else
+            "rank 0 NCCL-broadcasts all Gaussian buffers every frame (prefetched one frame ahead)")
+    exch = ("per-Gaussian gradient sums added straight into the owner rank's accumulator over NVLink peer "
+            "memory inside the blend kernel + one cross-GPU barrier kernel" if args.exchange == "peer" else
+            "partial [P,12] accumulators all_reduced by NCCL")
+    extra = {"parallelism": f"tile-row stripes x{world} ({'equal-height' if args.equal_stripes else 'balanced by per-row instance counts'}), "
+                            f"{mode}; {exch}; frame {'assembled on every rank (all_reduce)' if args.assemble else 'left in stripes'}; "
+                            f"gradients left with their owners",
+             "shard_mode": args.shard_mode, "exchange": args.exchange, "assemble": bool(args.assemble),
+             "ms_other_assembly_mode": ms_alt, "num_rendered_local_max": int(rmax.item()),
+             "stripe_bounds": bounds_h if not args.no_e2e else None, "check": check}
+    return dict(ms=ms, ms_fwd=ms_fwd, R=R_total, V=None, stages=stages, P=P, W=W, H=H, s=s, inp=inp,
+                grad_out=grad_out, e2e=e2e, extra=extra)
+
+
+# ------------------------------------------------------------------------------------------
 def run_gpu_arm(args, impl, rank, world, device):
     s = make_scene(args.workload, device)
     P, W, H = s.means3D.shape[0], s.img_w, s.img_h
@@ -192,61 +331,7 @@ def run_gpu_arm(args, impl, rank, world, device):
         from gaussiancity_b200 import _cabi, ext
         _cabi.lib()  # fail loudly if the CUDA library is missing
         if world > 1:
-            from gaussiancity_b200 import sharding
-            eng = sharding.TileShardedRasterizer(device=device)
-
-            # Two input buffer sets: frame i is rendered from set i%2 while the NCCL broadcast of
-            # frame i+1 (from rank 0, every frame, as north_star specifies) fills the other set on
-            # a side stream.  Every timed step still contains one full broadcast of all inputs.
-            big = ("means3D", "opacity", "scales", "rotations", "sh", "colors")
-            sets = [inp, {k: (v.clone() if k in big and v.numel() else v) for k, v in inp.items()}]
-            st = {"i": 0, "h": None}
-
-            def step_broadcast():
-                i = st["i"]
-                if st["h"] is None and i == 0:
-                    st["h"] = eng.start_prefetch(sets[0], src=0)
-                eng.wait_prefetch(st["h"])
-                nxt = eng.start_prefetch(sets[(i + 1) % 2], src=0)
-                out = eng.forward_backward_prefetched(s, sets[i % 2], grad_out)
-                st["i"], st["h"] = i + 1, nxt
-                return out
-
-            def step_replicated():
-                return eng.forward_backward_prefetched(s, inp, grad_out)
-            replicated = args.shard_mode == "replicated"
-            step = step_replicated if replicated else step_broadcast
-            fwd_only = (lambda: eng.render(inp, eng._cam(s, inp), broadcast=False)) if replicated else (lambda: eng.forward(s, inp, src=0))
-            ms = max_over_ranks(time_steps(step, args.steps, args.warmup, barrier), device, world)
-            ms_fwd = max_over_ranks(time_steps(fwd_only, max(2, args.steps // 2), 1, barrier), device, world)
-            R = eng.last_num_rendered_total
-            # e2e at N GPUs: rank 0 copies every input from pinned host memory, NCCL-broadcasts
-            # it, all ranks render/backward their tile rows, rank 0 reads image + loss back
-            e2e = None
-            if not args.no_e2e:
-                big_keys = [k for k in big if inp[k].numel()]
-                host = {k: inp[k].cpu().pin_memory() for k in big_keys} if rank == 0 else {}
-                host_img = torch.empty(3, H, W, dtype=torch.float32).pin_memory()
-                host_loss = torch.empty(1, dtype=torch.float32).pin_memory()
-                cam = eng._cam(s, inp)
-
-                def step_e2e():
-                    if rank == 0:
-                        for k in big_keys:
-                            inp[k].copy_(host[k], non_blocking=True)
-                    eng.broadcast_gaussians({k: inp[k] for k in big_keys}, src=0)
-                    color, radii, state = eng.render(inp, cam, broadcast=False)
-                    eng.backward(state, inp, cam, grad_out)
-                    if rank == 0:
-                        host_img.copy_(color, non_blocking=True)
-                        host_loss.copy_((color * grad_out).sum().reshape(1), non_blocking=True)
-                ms_e = max_over_ranks(time_steps(step_e2e, max(2, args.steps // 2), 2, barrier), device, world)
-                h2d = sum(inp[k].numel() * 4 for k in big_keys)
-                e2e = {"value": P / (ms_e * 1e-3) / 1e6, "unit": "Msplats/s", "ms_per_step": ms_e,
-                       "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(host_img.numel() * 4 + 4),
-                       "note": "rank 0 H2D + NCCL broadcast of all inputs every step, tile-sharded fwd+bwd"}
-            return dict(ms=ms, ms_fwd=ms_fwd, R=R, V=None, stages=None, P=P, W=W, H=H, s=s, inp=inp,
-                        grad_out=grad_out, e2e=e2e, extra={"parallelism": (f"tile-row shard x{world}, Gaussians resident on every rank (no per-frame broadcast): image all_reduce, [P,12] reduce_scatter, per-slice geometry backward" if replicated else f"tile-row shard x{world}: NCCL broadcast of all Gaussian buffers every frame (prefetched one frame ahead on a side stream), image all_reduce, [P,12] reduce_scatter, per-slice geometry backward")})
+            return run_sharded_arm(args, s, inp, grad_out, rank, world, device, barrier)
         mod = ext
     else:
         from tests import refext
@@ -366,12 +451,13 @@ def run_cpu_baseline(workload, budget_s=20.0):
     try:
         from oracle import torch_naive
         torch.set_num_threads(cores)
-        s1 = uniform_scene(1000, 128, 128, sh_degree=3, seed=0, device="cpu")
+        n1 = 100   # bounded sample of config 1 (the python loop over Gaussians costs ~50 ms each on a 128-core host)
+        s1 = uniform_scene(n1, 128, 128, sh_degree=3, seed=0, device="cpu")
         t1 = time.time()
         torch_naive.render_naive(s1)
         d1 = time.time() - t1
-        naive = {"workload": "config 1: 1k Gaussians, SH 3, 128x128, forward only", "seconds": d1,
-                 "Msplats_per_s_forward": 1000 / d1 / 1e6, "MPix_per_s": 128 * 128 / d1 / 1e6}
+        naive = {"workload": f"config 1 sample: {n1} of 1k Gaussians, SH 3, 128x128, forward only", "seconds": d1,
+                 "Msplats_per_s_forward": n1 / d1 / 1e6, "MPix_per_s": 128 * 128 / d1 / 1e6}
     except Exception as e:  # the reported baseline must never take the bench line down
         naive = {"error": repr(e)[:200]}
     return {"value": n / dt / 1e6, "unit": "Msplats/s", "cores": cores, "kind": "port",
@@ -390,9 +476,15 @@ def main():
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default=DEFAULT_WORKLOAD)
     ap.add_argument("--shard-mode", choices=["broadcast", "replicated"], default="replicated",
                     help="N>1: 'replicated' (default; consistent with `value` = inputs resident in HBM) = "
-                         "every rank holds the Gaussians, the exchange is the image all_reduce + the [P,12] "
-                         "gradient reduce_scatter; 'broadcast' = rank 0 owns them and NCCL-broadcasts all "
+                         "every rank holds the Gaussians; 'broadcast' = rank 0 owns them and NCCL-broadcasts all "
                          "buffers every frame (1.18 GB at the default workload: NVLink-bound, see DESIGN.md 5)")
+    ap.add_argument("--exchange", choices=["peer", "collective"], default="peer",
+                    help="N>1 gradient exchange: 'peer' = blend kernels add into the owner rank's accumulator over "
+                         "NVLink peer memory (default); 'collective' = NCCL all_reduce of partial accumulators")
+    ap.add_argument("--assemble", action="store_true", help="N>1: assemble the full frame on every rank inside the timed step")
+    ap.add_argument("--equal-stripes", action="store_true", help="N>1: equal-height stripes instead of balanced ones")
+    ap.add_argument("--remote-scalar", action="store_true", help="N>1 peer exchange: scalar atomics for remote accumulators")
+    ap.add_argument("--no-check", action="store_true", help="N>1: skip the untimed bit-identity gate")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -454,32 +546,38 @@ def main():
         if args.impl == "reference":
             line["impl"] = "reference"
             line["gpu_launches"] = 0
-            config["reference"] = "unmodified DGR CUDA extension (oracle/_ref) on 1 B200, native entry points"
+            line["impl_note"] = "unmodified DGR CUDA extension (oracle/_ref) on 1 B200, native entry points"
             line["cpu_baseline"] = {"value": value, "unit": "Msplats/s", "cores": 0, "kind": "reference",
                                     "sample": "full workload on the GPU: the reference has no CPU "
                                               "implementation of this path (SURVEY.md 8c)"}
         else:
             line["gpu_launches"] = kernels_per_step(W, H) * args.steps   # per rank
-            config.update(res["extra"])
-            if world_eff == 1:
-                config["parallelism"] = "single GPU"
+            line["parallelism"] = res["extra"].pop("parallelism", "single GPU")
+            if res["extra"]:
+                line["sharding"] = res["extra"]
         # roofline of the dominant kernel (per-stage CUDA events over the timed region)
         peak, peak_src = load_peaks()
         stages = res["stages"]
         if stages:
             T = ((W + 15) // 16) * ((H + 15) // 16)
             Npix = W * H
-            alg = {"blend_bwd": 8 * T + 40 * R + 20 * Npix + 44 * (V or 0),
-                   "blend_fwd": 8 * T + 40 * R + 20 * Npix}
+            Rk = R
+            if world_eff > 1:
+                # per launch on the slowest rank: its own stripe (instances: the largest stripe's count;
+                # tiles / pixels: 1/N of the frame; visible Gaussians of a stripe are not read back)
+                Rk = (line.get("sharding") or {}).get("num_rendered_local_max") or R // world_eff
+                T, Npix = T // world_eff, Npix // world_eff
+            alg = {"blend_bwd": 8 * T + 40 * Rk + 20 * Npix + 44 * (V or 0),
+                   "blend_fwd": 8 * T + 40 * Rk + 20 * Npix}
             dom = max(("blend_bwd", "blend_fwd"), key=lambda k: stages.get(k, 0.0))
             dur = stages[dom]
             achieved = alg[dom] / (dur * 1e-3) / 1e9
             traffic, issue = None, None
-            tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+            tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
             if os.path.exists(tpath):
                 with open(tpath) as fh:
                     tj = json.load(fh)
-                if tj.get("workload") == args.workload:   # per-launch DRAM bytes from the committed
+                if tj.get("workload") == args.workload and world_eff == 1:   # per-launch DRAM bytes from the committed
                     kj = tj["kernels"].get(dom, {})       # ncu --set full capture
                     traffic = kj.get("dram_bytes")
                     winst = kj.get("warp_instructions")

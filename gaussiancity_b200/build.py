@@ -82,6 +82,53 @@ def build_library(force=False, verbose=False, ptxas_info=False):
     return LIB_PATH
 
 
+# ---- Seam A: the native module `diff_gaussian_rasterization_ext` (csrc/torch_module.cpp) -----------
+MODNAME = "diff_gaussian_rasterization_ext"
+COMPAT_DIR = os.path.join(PKG_DIR, "compat")
+
+
+def native_module_path():
+    import sysconfig
+    return os.path.join(COMPAT_DIR, MODNAME + sysconfig.get_config_var("EXT_SUFFIX"))
+
+
+def build_native_module(force=False, verbose=False):
+    """g++ only (host code over the C ABI; ~1-2 min of torch headers).  The module links
+    libgcr_rasterizer.so through an $ORIGIN-relative rpath, so the pair travels together."""
+    import sysconfig
+    build_library()
+    out = native_module_path()
+    src = os.path.join(CSRC, "torch_module.cpp")
+    hdr = os.path.join(ROOT, "include", "gcr_rasterizer.h")
+    stamp = os.path.join(COMPAT_DIR, ".native.stamp")
+    h = hashlib.sha256()
+    for f in (src, hdr):
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    import torch
+    h.update(torch.__version__.encode())
+    fp = h.hexdigest()
+    if not force and os.path.exists(out) and os.path.exists(stamp) and open(stamp).read().strip() == fp:
+        return out
+    from torch.utils import cpp_extension as ce
+    os.makedirs(COMPAT_DIR, exist_ok=True)
+    incs = ce.include_paths() + [sysconfig.get_paths()["include"], "/usr/local/cuda/include"]
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", f"-DTORCH_EXTENSION_NAME={MODNAME}",
+           "-DTORCH_API_INCLUDE_EXTENSION_H", "-D_GLIBCXX_USE_CXX11_ABI=1"] + [f"-I{p}" for p in incs] + \
+          [src, "-o", out, f"-L{PKG_DIR}", "-lgcr_rasterizer", "-Wl,-rpath,$ORIGIN/.."]
+    for d in ce.library_paths():
+        cmd += [f"-L{d}", f"-Wl,-rpath,{d}"]
+    cmd += ["-lc10", "-ltorch_cpu", "-ltorch", "-ltorch_python", "-lc10_cuda", "-ltorch_cuda"]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    with open(stamp, "w") as fh:
+        fh.write(fp)
+    return out
+
+
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv,
                         ptxas_info="--ptxas" in sys.argv))
+    if "--native" in sys.argv:
+        print(build_native_module(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -131,7 +131,7 @@ struct Carver {
 };
 
 struct GeomLayout {
-  size_t keys_a, keys_b, vals_a, vals_b, tiles, records, clamped, owner, offsets, grad_acc, radii,
+  size_t keys_a, keys_b, vals_a, vals_b, tiles, records, rects, clamped, owner, offsets, grad_acc, radii,
       zero_begin, counters, sort_ws, emit_ws, zero_end, total;
   explicit GeomLayout(size_t P) {
     Carver c;
@@ -141,6 +141,7 @@ struct GeomLayout {
     vals_b = c.take(4 * P);
     tiles = c.take(4 * P);
     records = c.take(48 * P);
+    rects = c.take(8 * P);
     clamped = c.take(P);
     owner = c.take(P);
     offsets = c.take(4 * P);
@@ -297,7 +298,7 @@ int forward_impl(gcr_alloc_fn geometryBuffer, void* geometry_ctx, gcr_alloc_fn b
   pa.shard_rank = shard_rank; pa.shard_count = shard_count; pa.stripe_bounds = bounds_dev;
   pa.prefiltered = prefiltered != 0;
   pa.radii = radii; pa.tiles_touched = tiles_touched; pa.depth_keys = keys_a;
-  pa.records = records; pa.clamped = reinterpret_cast<uint8_t*>(gptr + gl.clamped);
+  pa.records = records; pa.rects = reinterpret_cast<uint2*>(gptr + gl.rects); pa.clamped = reinterpret_cast<uint8_t*>(gptr + gl.clamped);
   pa.owner = reinterpret_cast<uint8_t*>(gptr + gl.owner);
   pa.total_tiles = reinterpret_cast<unsigned long long*>(counters + GCR_CNT_TOTAL_TILES64);
   pa.dbg_cov3D = g_dbg_cov3d;
@@ -357,8 +358,7 @@ int forward_impl(gcr_alloc_fn geometryBuffer, void* geometry_ctx, gcr_alloc_fn b
     GcrEmitLaunch el;
     memset(&el, 0, sizeof(el));
     el.n_max = (uint32_t)P; el.n_vis = counters + GCR_CNT_NVIS; el.sorted_gauss = sorted_gauss;
-    el.tiles_touched = tiles_touched; el.records = records; el.radii = radii;
-    el.grid_x = grid_x; el.grid_y = grid_y; el.stripe = stripe;
+    el.rects = reinterpret_cast<const uint2*>(gptr + gl.rects); el.grid_x = grid_x;
     el.tile_keys = k_in; el.gauss_vals = v_in; el.cap = (uint32_t)R;
     el.workspace = gptr + gl.emit_ws; el.ghist_tile = gcr_sort_ghist(tile_ws); el.tile_end_bit = tbits;
     el.counters = counters; el.offsets_out = reinterpret_cast<uint32_t*>(gptr + gl.offsets);

@@ -318,11 +318,8 @@ struct EmitArgs {
   uint32_t n_max;                 // upper bound of visible Gaussians (P)
   const uint32_t* n_vis;          // device count
   const uint32_t* sorted_gauss;
-  const uint32_t* tiles_touched;
-  const GcrRecord* records;
-  const int* radii;
-  int grid_x, grid_y;
-  const int* stripe;              // device {row0,row1} or null = all rows
+  const uint2* rects;             // x0 | y0 << 16, width | rows << 16 (stripe-clipped)
+  int grid_x;
   uint32_t* tile_keys;
   uint32_t* gauss_vals;
   uint32_t cap;                   // capacity of tile_keys / gauss_vals
@@ -346,7 +343,6 @@ emit_scan_kernel(EmitArgs a) {
   for (int p = 0; p < kMaxPasses; ++p) hist[p][tid] = 0;
   const uint32_t n_vis = load_count(a.n_vis, a.n_max);
   const uint32_t nchunks = (n_vis + kEmitThreads - 1) / kEmitThreads;
-  const int row0 = a.stripe != nullptr ? a.stripe[0] : 0;   // first owned tile row
   __syncthreads();
 
   while (true) {
@@ -364,15 +360,11 @@ emit_scan_kernel(EmitArgs a) {
     uint32_t g = 0, n = 0, x0 = 0, w = 1, y0 = 0;
     if (i < n_vis) {
       g = a.sorted_gauss[i];
-      n = a.tiles_touched[g];
-      if (n != 0) {
-        const float4 q0 = a.records[g].q0;
-        uint2 rmin, rmax;
-        gcr_get_rect(q0.x, q0.y, a.radii[g], a.grid_x, a.grid_y, rmin, rmax);
-        x0 = rmin.x;
-        w = rmax.x - rmin.x;
-        y0 = max((int)rmin.y, row0);
-      }
+      const uint2 rc = a.rects[g];   // one 8-byte gather per Gaussian (every listed one has tiles)
+      x0 = rc.x & 0xFFFFu;
+      y0 = rc.x >> 16;
+      w = rc.y & 0xFFFFu;
+      n = w * (rc.y >> 16);
     }
     // chunk-local inclusive scan of the tile counts
     const uint32_t winc = warp_incl_scan(n, lane);
@@ -566,8 +558,7 @@ cudaError_t gcr_launch_emit_scan(const GcrEmitLaunch& l, cudaStream_t stream) {
   if (l.n_max == 0) return cudaSuccess;
   EmitArgs a;
   a.n_max = l.n_max; a.n_vis = l.n_vis; a.sorted_gauss = l.sorted_gauss;
-  a.tiles_touched = l.tiles_touched; a.records = l.records; a.radii = l.radii;
-  a.grid_x = l.grid_x; a.grid_y = l.grid_y; a.stripe = l.stripe;
+  a.rects = l.rects; a.grid_x = l.grid_x;
   a.tile_keys = l.tile_keys; a.gauss_vals = l.gauss_vals; a.cap = l.cap;
   uint32_t* ws = static_cast<uint32_t*>(l.workspace);
   a.ticket = ws;
@@ -575,7 +566,7 @@ cudaError_t gcr_launch_emit_scan(const GcrEmitLaunch& l, cudaStream_t stream) {
   a.ghist_tile = l.ghist_tile; a.tile_end_bit = l.tile_end_bit <= 0 ? 1 : l.tile_end_bit;
   a.counters = l.counters; a.offsets_out = l.offsets_out;
   const unsigned chunks = (l.n_max + kEmitThreads - 1) / kEmitThreads;
-  const unsigned grid = chunks < 148u * 6u ? chunks : 148u * 6u;   // persistent: 6 CTAs per SM
+  const unsigned grid = chunks < 148u * 8u ? chunks : 148u * 8u;   // persistent: 8 CTAs per SM
   emit_scan_kernel<<<grid, kEmitThreads, 0, stream>>>(a);
   return cudaGetLastError();
 }

@@ -41,6 +41,7 @@ struct GcrPreprocessArgs {
   uint32_t* tiles_touched;  // tiles inside this rank's stripe
   uint32_t* depth_keys;     // 0xFFFFFFFF unless the Gaussian touches this rank's stripe
   GcrRecord* records;
+  uint2* rects;             // stripe-clipped tile rect, packed (written when tiles_touched > 0)
   uint8_t* clamped;
   uint8_t* owner;           // rank whose stripe holds the centre row (GCR_NO_OWNER if culled)
   unsigned long long* total_tiles;  // zeroed; += sum of tiles_touched (= num_rendered)
@@ -82,11 +83,8 @@ struct GcrEmitLaunch {
   uint32_t n_max;
   const uint32_t* n_vis;
   const uint32_t* sorted_gauss;
-  const uint32_t* tiles_touched;
-  const GcrRecord* records;
-  const int* radii;
-  int grid_x, grid_y;
-  const int* stripe;       // device {row0,row1} or null
+  const uint2* rects;      // packed stripe-clipped tile rects from the preprocess
+  int grid_x;
   uint32_t* tile_keys;
   uint32_t* gauss_vals;
   uint32_t cap;

@@ -195,6 +195,8 @@ __forceinline__ __device__ uint32_t preprocess_one(const GcrPreprocessArgs& a, c
     const int y0 = max((int)g.rmin.y, row0), y1 = min((int)g.rmax.y, row1);
     if (y1 > y0) {
       tiles = (g.rmax.x - g.rmin.x) * (uint32_t)(y1 - y0);
+      // the emit stage needs only this word per Gaussian: x0 | y0 << 16, width | rows << 16
+      a.rects[idx] = make_uint2(g.rmin.x | ((uint32_t)y0 << 16), (g.rmax.x - g.rmin.x) | ((uint32_t)(y1 - y0) << 16));
       {
         // colour: SH evaluation (forward.cu:20-66) or precomputed
         float cr, cg, cb;

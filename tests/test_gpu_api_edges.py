@@ -81,6 +81,50 @@ def test_wrapper_city_frame_matches_reference_and_oracle(built_lib, cuda_device)
         assert torch.equal(torch.flip(img, dims=[2]), col_ref)     # precomputed colours: bit-exact
 
 
+def test_wrapper_city_frame_gradients_match_reference(built_lib, cuda_device):
+    """The gradients GaussianCity actually trains on: 40 k lattice points with opacity 1, identity
+    quaternions and many exact depth ties, seen through the K / sensor camera with negative
+    clip-space w.  All eight gradient tensors of the backward are compared with the unmodified
+    reference extension (<= 1e-4 norm-relative), after a bit-exact forward; and the autograd path
+    through the public wrapper ([N,14] points in, image out) reproduces them."""
+    ref = refext.load_reference_ext()
+    assert ref is not None, "oracle/_ref is not built"
+    pts, cam_pos, cam_quat = city_points(40_000, seed=4, device=cuda_device)
+    wrap = g.GaussianRasterizerWrapper(CITY_K, CITY_SENSOR, device=cuda_device)
+    st = wrap._get_gaussian_rasterization_settings(cam_pos, cam_quat)
+    e = torch.Tensor([])
+    P, H, W = pts.shape[0], 540, 960
+    cols = [pts[:, 0:3].contiguous(), pts[:, 11:14].contiguous(), pts[:, 3:4].contiguous(),
+            pts[:, 4:7].contiguous(), pts[:, 7:11].contiguous()]
+    fargs = (st.bg, cols[0], cols[1], cols[2], cols[3], cols[4], 1.0, e, st.view_matrix, st.proj_matrix,
+             st.tanfovx, st.tanfovy, H, W, e, 0, st.campos, False, False)
+    R_ref, col_ref, rad_ref, geom_ref, bin_ref, img_ref = ref.rasterize_gaussians(*fargs)
+    R, col, rad, geom, binning, img = ours.rasterize_gaussians(*fargs)
+    assert R == R_ref and torch.equal(rad, rad_ref) and torch.equal(col, col_ref)
+    ov = refext.our_views(P, R, W, H, geom, binning, img)
+    assert torch.equal(ov["point_list"], refext.ref_binning_views(bin_ref, R)["point_list"])   # ties included
+    assert int((rad > 0).sum()) > 10_000
+    G = torch.randn(3, H, W, generator=torch.Generator().manual_seed(12)).to(cuda_device)
+    bargs = lambda r_, gm, n, bn, im: (st.bg, cols[0], r_, cols[1], cols[3], cols[4], 1.0, e, st.view_matrix,
+                                        st.proj_matrix, st.tanfovx, st.tanfovy, G, e, 0, st.campos, gm, n, bn, im, False)
+    gr = ref.rasterize_gaussians_backward(*bargs(rad_ref, geom_ref, R_ref, bin_ref, img_ref))
+    go = ours.rasterize_gaussians_backward(*bargs(rad, geom, R, binning, img))
+    torch.cuda.synchronize()
+    names = ["dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dcov3D", "dL_dsh", "dL_dscales",
+             "dL_drotations"]
+    rel = lambda a, b: (a.double() - b.double()).norm().item() / max(b.double().norm().item(), 1e-30)
+    for n, a, b in zip(names, go, gr):
+        assert a.shape == b.shape, n
+        if b.numel():
+            assert torch.isfinite(a).all() and rel(a, b) <= 1e-4, f"{n}: {rel(a, b)}"
+    # the same numbers through the public wrapper + autograd (image is flipped along W on the way out)
+    leaf = pts.clone().requires_grad_(True)
+    out = wrap(leaf, cam_pos, cam_quat)
+    (out * torch.flip(G, dims=[2])).sum().backward()
+    packed = torch.cat([go[3], go[2], go[6], go[7], go[1]], dim=1)      # xyz | opacity | scale | quat | rgb
+    assert rel(leaf.grad, packed) <= 1e-5
+
+
 def test_empty_and_fully_culled_inputs(built_lib, cuda_device):
     s = uniform_scene(64, 48, 40, seed=1, device=cuda_device, bg=(0.5, 0.25, 0.125))
     e = torch.Tensor([])
