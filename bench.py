@@ -277,8 +277,9 @@ def run_sharded_arm(args, s, inp, grad_out, rank, world, device, barrier):
         host = {k: inp[k][lo:hi].cpu().pin_memory() for k in big_keys}
         slab = {k: torch.zeros((per,) + tuple(inp[k].shape[1:]), **opts) for k in big_keys}
         gathered = {k: torch.empty((per * world,) + tuple(inp[k].shape[1:]), **opts) for k in big_keys}
-        bounds_h = eng.stripes(inp, cam)
-        bounds_h = bounds_h.cpu().tolist() if bounds_h is not None else sharding.equal_stripes((H + 15) // 16, world)
+        _c, _r, st0 = eng.render(inp, cam, assemble=False)
+        bounds_h = eng.backend.stripe_bounds(st0, inp, world).cpu().tolist()
+        del _c, _r, st0
         r0, r1 = bounds_h[rank] * 16, min(H, bounds_h[rank + 1] * 16)
         host_img = torch.empty(3, max(1, r1 - r0), W, dtype=torch.float32).pin_memory()
         host_loss = torch.empty(1, dtype=torch.float32).pin_memory()
@@ -332,7 +333,9 @@ def run_gpu_arm(args, impl, rank, world, device):
         _cabi.lib()  # fail loudly if the CUDA library is missing
         if world > 1:
             return run_sharded_arm(args, s, inp, grad_out, rank, world, device, barrier)
-        mod = ext
+        import gaussiancity_b200 as pkg
+        mod = pkg.dgr_ext                      # the binding the public operator surface uses
+        extra["host_binding"] = pkg.HOST_BINDING
     else:
         from tests import refext
         mod = refext.load_reference_ext()

@@ -17,8 +17,36 @@ import typing
 import numpy as np
 import torch
 
-from . import ext as dgr_ext
+from . import ext as _ctypes_ext
 from .camera import PoseSettingsCache, w2c_host
+
+# Host binding of the three native entry points.  Both bindings are thin layers over the same C
+# ABI (include/gcr_rasterizer.h) and the same CUDA library -- there is no CPU path behind either:
+#   compat/diff_gaussian_rasterization_ext  native torch module (csrc/torch_module.cpp): what the
+#       reference's own Python imports (Seam A); ~10 us of host time per call, which is what counts
+#       in GaussianCity's own regime (<= 16 384 points per frame, launch/host bound);
+#   ext.py  ctypes: no compiler needed beyond nvcc, carries the striped (multi-GPU) extensions.
+# GCR_HOST_BINDING=ctypes|native forces one (native raises if it has not been built).
+import os as _os
+
+
+def _pick_binding():
+    want = _os.environ.get("GCR_HOST_BINDING", "")
+    if want == "ctypes":
+        return _ctypes_ext, "ctypes"
+    try:
+        from .compat import diff_gaussian_rasterization_ext as native
+        if native.abi_version() == _ctypes_ext._cabi.ABI_VERSION:
+            return native, "native"
+        if want == "native":
+            raise ImportError("native module was built against another ABI version: rebuild")
+    except ImportError:
+        if want == "native":
+            raise
+    return _ctypes_ext, "ctypes"
+
+
+dgr_ext, HOST_BINDING = _pick_binding()
 
 __all__ = [
     "RasterizeGaussiansFunction",

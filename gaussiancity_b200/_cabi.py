@@ -65,7 +65,7 @@ def _declare(l):
     l.gcr_rasterizer_forward.restype = c_int
     l.gcr_rasterizer_forward.argtypes = fwd_args + [c_void_p]
     l.gcr_rasterizer_forward_striped.restype = c_int
-    l.gcr_rasterizer_forward_striped.argtypes = fwd_args + [c_void_p, c_void_p]
+    l.gcr_rasterizer_forward_striped.argtypes = fwd_args + [c_void_p, c_int, c_void_p]
     l.gcr_rasterizer_backward.restype = c_int
     l.gcr_rasterizer_backward.argtypes = (
         [c_int] * 4 + [c_void_p, c_int, c_int] + [c_void_p] * 4 + [c_float] + [c_void_p] * 5 +

@@ -35,10 +35,10 @@ thread_local float* g_dbg_cov3d = nullptr;  // test hook: next forward also writ
 // ---- optional per-stage timing with CUDA events recorded on the caller's stream (no host
 // sync is added; bench.py reads the elapsed times after it has synchronised) -----------------
 enum Stage {
-  ST_PREPROCESS = 0, ST_DEPTH_SORT, ST_EMIT, ST_TILE_SORT, ST_RANGES, ST_BLEND_FWD,
+  ST_PREPROCESS = 0, ST_SELECT, ST_DEPTH_SORT, ST_EMIT, ST_TILE_SORT, ST_RANGES, ST_BLEND_FWD,
   ST_BWD_ZERO, ST_BLEND_BWD, ST_GEOM_BWD, ST_PARTITION, ST_COUNT
 };
-const char* const kStageNames[ST_COUNT] = {"preprocess_fwd", "depth_sort", "scan_emit", "tile_sort",
+const char* const kStageNames[ST_COUNT] = {"preprocess_fwd", "stripe_select", "depth_sort", "scan_emit", "tile_sort",
                                            "tile_ranges", "blend_fwd", "bwd_zero", "blend_bwd",
                                            "geometry_bwd", "stripe_partition"};
 constexpr int kProfSlots = 64;  // ring of profiled forward(+backward) calls
@@ -131,8 +131,8 @@ struct Carver {
 };
 
 struct GeomLayout {
-  size_t keys_a, keys_b, vals_a, vals_b, tiles, records, rects, clamped, owner, offsets, grad_acc, radii,
-      zero_begin, counters, sort_ws, emit_ws, zero_end, total;
+  size_t keys_a, keys_b, vals_a, vals_b, tiles, records, rects, packed_rects, clamped, owner, offsets, grad_acc,
+      radii, zero_begin, counters, row_hist, sort_ws, emit_ws, zero_end, total;
   explicit GeomLayout(size_t P) {
     Carver c;
     keys_a = c.take(4 * P);
@@ -142,6 +142,7 @@ struct GeomLayout {
     tiles = c.take(4 * P);
     records = c.take(48 * P);
     rects = c.take(8 * P);
+    packed_rects = c.take(8 * P);
     clamped = c.take(P);
     owner = c.take(P);
     offsets = c.take(4 * P);
@@ -149,6 +150,7 @@ struct GeomLayout {
     radii = c.take(4 * P);
     // one contiguous block zeroed by a single memset per forward: counters + both workspaces
     counters = zero_begin = c.take(GCR_CNT_WORDS * sizeof(uint32_t));
+    row_hist = c.take((4096 + 1) * sizeof(uint32_t));   // instances per tile row (+1: done-CTA ticket)
     sort_ws = c.take(gcr_sort_workspace_bytes(P));
     emit_ws = c.take(gcr_emit_workspace_bytes(P));
     zero_end = gcr_align_up(c.off, 256);
@@ -209,7 +211,7 @@ int forward_impl(gcr_alloc_fn geometryBuffer, void* geometry_ctx, gcr_alloc_fn b
                  const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
                  const float* cam_pos, float tan_fovx, float tan_fovy, int prefiltered,
                  float* out_color, int* radii, int debug, int shard_rank, int shard_count,
-                 const int* stripe_bounds, void* cuda_stream) {
+                 const int* stripe_bounds, int balanced, void* cuda_stream) {
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
   if (P <= 0) return 0;
   prof_next_call();
@@ -240,6 +242,7 @@ int forward_impl(gcr_alloc_fn geometryBuffer, void* geometry_ctx, gcr_alloc_fn b
   const int grid_y = (height + GCR_TILE_Y - 1) / GCR_TILE_Y;
   const int tiles = grid_x * grid_y;
   const size_t npix = (size_t)width * height;
+  if (grid_x > 4095 || grid_y > 4095) return fail("images above 65520 pixels a side are not supported");
   int dev = 0;
   GCR_CUDA_OK(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) return fail("device ordinal out of range");
@@ -269,11 +272,14 @@ int forward_impl(gcr_alloc_fn geometryBuffer, void* geometry_ctx, gcr_alloc_fn b
   GCR_CUDA_OK(cudaMemsetAsync(ranges, 0, sizeof(uint2) * (size_t)tiles, stream));
   // the stripe bounds travel with the geometry buffer (the backward reads them from there)
   int* bounds_dev = nullptr;
+  bool deferred = false;   // balanced stripes cut on the device from this frame's own rects
   if (shard_count > 1) {
     bounds_dev = reinterpret_cast<int*>(counters + GCR_CNT_STRIPE_BOUNDS);
     if (stripe_bounds != nullptr) {
       GCR_CUDA_OK(cudaMemcpyAsync(bounds_dev, stripe_bounds, sizeof(int) * (shard_count + 1),
                                   cudaMemcpyDeviceToDevice, stream));
+    } else if (balanced) {
+      deferred = true;
     } else {
       int eq[GCR_MAX_SHARDS + 1];
       for (int k = 0; k <= shard_count; ++k) eq[k] = (int)((long long)grid_y * k / shard_count);
@@ -283,7 +289,7 @@ int forward_impl(gcr_alloc_fn geometryBuffer, void* geometry_ctx, gcr_alloc_fn b
   }
   const int* stripe = bounds_dev != nullptr ? bounds_dev + shard_rank : nullptr;
 
-  // 1. per-Gaussian preprocessing
+  // 1. per-Gaussian projection (+ stripe selection)
   GcrPreprocessArgs pa;
   memset(&pa, 0, sizeof(pa));
   pa.P = P; pa.D = D; pa.M = M;
@@ -298,14 +304,23 @@ int forward_impl(gcr_alloc_fn geometryBuffer, void* geometry_ctx, gcr_alloc_fn b
   pa.shard_rank = shard_rank; pa.shard_count = shard_count; pa.stripe_bounds = bounds_dev;
   pa.prefiltered = prefiltered != 0;
   pa.radii = radii; pa.tiles_touched = tiles_touched; pa.depth_keys = keys_a;
-  pa.records = records; pa.rects = reinterpret_cast<uint2*>(gptr + gl.rects); pa.clamped = reinterpret_cast<uint8_t*>(gptr + gl.clamped);
+  pa.records = records; pa.rects = reinterpret_cast<uint2*>(gptr + gl.rects);
+  pa.clamped = reinterpret_cast<uint8_t*>(gptr + gl.clamped);
   pa.owner = reinterpret_cast<uint8_t*>(gptr + gl.owner);
   pa.total_tiles = reinterpret_cast<unsigned long long*>(counters + GCR_CNT_TOTAL_TILES64);
+  pa.packed_rects = reinterpret_cast<unsigned long long*>(gptr + gl.packed_rects);
+  pa.row_hist = reinterpret_cast<uint32_t*>(gptr + gl.row_hist);
+  pa.stripe_bounds_out = bounds_dev;
   pa.dbg_cov3D = g_dbg_cov3d;
   g_dbg_cov3d = nullptr;
   prof_mark(ST_PREPROCESS, 0, stream);
-  GCR_LAUNCH("preprocess_fwd", gcr_launch_preprocess_fwd(pa, stream), debug, stream);
+  GCR_LAUNCH("project", gcr_launch_project(pa, deferred, stream), debug, stream);
   prof_mark(ST_PREPROCESS, 1, stream);
+  if (deferred) {
+    prof_mark(ST_SELECT, 0, stream);
+    GCR_LAUNCH("stripe select", gcr_launch_stripe_select(pa, stream), debug, stream);
+    prof_mark(ST_SELECT, 1, stream);
+  }
 
   // num_rendered on its way to the host; the wait comes after the depth sort is enqueued
   HostMailbox& mb = g_mailbox;
@@ -415,7 +430,7 @@ int gcr_rasterizer_forward(gcr_alloc_fn geometryBuffer, void* geometry_ctx,
                       P, D, M, background, width, height, means3D, shs, colors_precomp, opacities,
                       scales, scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix, cam_pos,
                       tan_fovx, tan_fovy, prefiltered, out_color, radii, debug, shard_rank, shard_count,
-                      nullptr, cuda_stream);
+                      nullptr, 0, cuda_stream);
 }
 
 int gcr_rasterizer_forward_striped(gcr_alloc_fn geometryBuffer, void* geometry_ctx,
@@ -430,12 +445,12 @@ int gcr_rasterizer_forward_striped(gcr_alloc_fn geometryBuffer, void* geometry_c
                                    const float* cam_pos, float tan_fovx, float tan_fovy,
                                    int prefiltered, float* out_color, int* radii, int debug,
                                    int shard_rank, int shard_count, const int* stripe_bounds,
-                                   void* cuda_stream) {
+                                   int balanced, void* cuda_stream) {
   return forward_impl(geometryBuffer, geometry_ctx, binningBuffer, binning_ctx, imageBuffer, image_ctx,
                       P, D, M, background, width, height, means3D, shs, colors_precomp, opacities,
                       scales, scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix, cam_pos,
                       tan_fovx, tan_fovy, prefiltered, out_color, radii, debug, shard_rank, shard_count,
-                      stripe_bounds, cuda_stream);
+                      stripe_bounds, balanced, cuda_stream);
 }
 
 int gcr_rasterizer_backward_blend(int P, int R, const float* background, int width, int height,
@@ -457,6 +472,8 @@ int gcr_rasterizer_backward_blend(int P, int R, const float* background, int wid
   if (geom_buffer == nullptr || image_buffer == nullptr || dL_dpix == nullptr || background == nullptr)
     return fail("geom_buffer, image_buffer, dL_dpix and background must not be NULL");
   if (R > 0 && binning_buffer == nullptr) return fail("binning_buffer must not be NULL when R > 0");
+  if (n_accumulators > 1 && P >= (1 << 27))
+    return fail("per-rank accumulators support up to 2^27 Gaussians (owner rank is packed into the id)");
   float* local = accumulators[n_accumulators == 1 ? 0 : shard_rank];
   if (zero_first) {
     prof_mark(ST_BWD_ZERO, 0, stream);
@@ -480,6 +497,7 @@ int gcr_rasterizer_backward_blend(int P, int R, const float* background, int wid
   ba.ranges = reinterpret_cast<const uint2*>(iptr + il.ranges);
   ba.point_list = reinterpret_cast<const uint32_t*>(bptr);   // BinLayout::vals_a == 0
   ba.records = reinterpret_cast<const GcrRecord*>(gptr + gl.records);
+  ba.owner = reinterpret_cast<const uint8_t*>(gptr + gl.owner);
   ba.bg = background;
   ba.final_T = reinterpret_cast<float*>(iptr + il.final_T);
   ba.n_contrib = reinterpret_cast<uint32_t*>(iptr + il.n_contrib);
@@ -630,6 +648,7 @@ int gcr_stripe_partition(int P, const float* means3D, const float* scales, float
     return fail("workspace and stripe_bounds_out must not be NULL");
   const int grid_x = (width + GCR_TILE_X - 1) / GCR_TILE_X;
   const int grid_y = (height + GCR_TILE_Y - 1) / GCR_TILE_Y;
+  if (grid_x > 4095 || grid_y > 4095) return fail("images above 65520 pixels a side are not supported");
   if (P <= 0) {
     int eq[GCR_MAX_SHARDS + 1];
     for (int k = 0; k <= shard_count; ++k) eq[k] = (int)((long long)grid_y * k / shard_count);
@@ -654,11 +673,11 @@ int gcr_stripe_partition(int P, const float* means3D, const float* scales, float
   pa.focal_x = width / (2.0f * tan_fovx);
   pa.grid_x = grid_x; pa.grid_y = grid_y;
   pa.shard_rank = 0; pa.shard_count = shard_count;
+  pa.row_hist = static_cast<uint32_t*>(workspace);
+  pa.stripe_bounds_out = stripe_bounds_out;
   GCR_CUDA_OK(cudaMemsetAsync(workspace, 0, sizeof(uint32_t) * (size_t)(grid_y + 1), stream));
   prof_mark(ST_PARTITION, 0, stream);
-  GCR_LAUNCH("stripe partition",
-             gcr_launch_stripe_partition(pa, static_cast<uint32_t*>(workspace), stripe_bounds_out, stream), 0,
-             stream);
+  GCR_LAUNCH("stripe partition", gcr_launch_stripe_partition(pa, stream), 0, stream);
   prof_mark(ST_PARTITION, 1, stream);
   return 0;
 }

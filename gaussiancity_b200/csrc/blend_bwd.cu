@@ -33,8 +33,12 @@ namespace {
 constexpr int kSlots = 8;                       // records per panel
 constexpr int kPanelStride = 33;                // padded pixel stride (bank-conflict free)
 constexpr int kWarpPanelFloats = 3 * kSlots * kPanelStride;            // 792
-constexpr int kWarpScratchBytes = 3840;         // panel 3168 + slot_j 32 + pixel consts 576, padded
-constexpr int kBwdSmemBytes = kBlendStages * kBlendBatch * (int)sizeof(GcrRecord) + 8 * kWarpScratchBytes + 64;
+constexpr int kWarpScratchBytes = 3776;         // panel 3168 + slot_j 32 + pixel consts 576
+// stage ring | 8 warp scratch areas | barriers + s_max_last (64 B) | per-stage Gaussian ids.
+// 56 896 B: four CTAs per SM still fit (4 x (56 896 + 1 024 reserved) <= 228 KB).
+constexpr int kBwdSmemBytes = kBlendStages * kBlendBatch * (int)sizeof(GcrRecord) + 8 * kWarpScratchBytes + 64 +
+                              kBlendStages * kBlendBatch * (int)sizeof(uint32_t);
+constexpr int kOwnerShift = 27;   // striped frames: owner rank in the top 5 bits of the staged id
 
 // Math: the gradients only have to meet the 1e-4 bar, so exp is ex2.approx(power * log2 e)
 // (2 instructions instead of ~10) and 1/(1-alpha) one MUFU.RCP (instead of the IEEE reciprocal's
@@ -43,13 +47,18 @@ constexpr int kBwdSmemBytes = kBlendStages * kBlendBatch * (int)sizeof(GcrRecord
 // flipped alpha >= 1/255 decision would rescale the rest of that pixel's T chain), so any alpha
 // within 1e-7 of the threshold -- 30x the worst-case error of the approximation there -- is
 // re-evaluated with the exact expf.
-__global__ void __launch_bounds__(kBlendThreads)
+__global__ void __launch_bounds__(kBlendThreads, 4)   // 64 registers: 4 CTAs/SM (shared memory allows 4)
 blend_bwd_kernel(GcrBlendArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   GcrRecord (*stage)[kBlendBatch] = reinterpret_cast<GcrRecord (*)[kBlendBatch]>(smem_raw);
   unsigned char* scratch0 = smem_raw + kBlendStages * kBlendBatch * sizeof(GcrRecord);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(scratch0 + 8 * kWarpScratchBytes);
   int* s_max_last_p = reinterpret_cast<int*>(full_bar + kBlendStages);
+  // which Gaussian each staged record belongs to (= its accumulator row); on striped frames with
+  // per-rank accumulators the owner rank rides in the top 5 bits (api.cu bounds P accordingly)
+  uint32_t (*stage_id)[kBlendBatch] =
+      reinterpret_cast<uint32_t (*)[kBlendBatch]>(scratch0 + 8 * kWarpScratchBytes + 64);
+  const bool striped = a.n_acc > 1;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float* panel = reinterpret_cast<float*>(scratch0 + warp * kWarpScratchBytes);
@@ -111,8 +120,15 @@ blend_bwd_kernel(GcrBlendArgs a) {
     const int j = max(0, hi - kBlendBatch) + tid;
     return j < hi ? (int)ids[j] : -1;
   };
-  if (nb > 0) gcr_gather_record(&stage[0][tid], a.records, batch_id(0), &full_bar[0]);
+  if (nb > 0) {
+    const int id0 = batch_id(0);
+    gcr_gather_record(&stage[0][tid], a.records, id0, &full_bar[0]);
+    uint32_t tag = (uint32_t)id0;
+    if (striped && id0 >= 0) tag |= (uint32_t)a.owner[id0] << kOwnerShift;
+    stage_id[0][tid] = tag;
+  }
   int next_id = batch_id(1);
+  __syncthreads();   // stage_id / stage_owner of batch 0
 
   float T = T_final;
   float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
@@ -127,8 +143,12 @@ blend_bwd_kernel(GcrBlendArgs a) {
 
   for (int b = 0; b < nb; ++b) {
     const int s = b & 1;
+    uint32_t fetched_tag = 0;
     if (b + 1 < nb) {
       gcr_gather_record(&stage[s ^ 1][tid], a.records, next_id, &full_bar[s ^ 1]);
+      fetched_tag = (uint32_t)next_id;
+      // consumed at the end of this batch: the load's latency hides behind the batch's work
+      if (striped && next_id >= 0) fetched_tag |= (uint32_t)a.owner[next_id] << kOwnerShift;
       next_id = batch_id(b + 2);
     }
     gcr_mbar_wait(&full_bar[s], (uint32_t)((b >> 1) & 1));
@@ -149,8 +169,11 @@ blend_bwd_kernel(GcrBlendArgs a) {
         const int jj = slot_j[rB];
         const float4 r0 = st[jj].q0;
         const float2 r1 = *reinterpret_cast<const float2*>(&st[jj].q1);
-        gidx = __float_as_uint(st[jj].q2.y);
-        owner = a.n_acc > 1 ? (int)__float_as_uint(st[jj].q2.w) : 0;
+        gidx = stage_id[s][jj];
+        if (striped) {
+          owner = (int)(gidx >> kOwnerShift);
+          gidx &= (1u << kOwnerShift) - 1u;
+        }
         const float* wa = panel + (0 * kSlots + rB) * kPanelStride + qB * 8;
         const float* wb = panel + (1 * kSlots + rB) * kPanelStride + qB * 8;
         const float* wg = panel + (2 * kSlots + rB) * kPanelStride + qB * 8;
@@ -213,10 +236,9 @@ blend_bwd_kernel(GcrBlendArgs a) {
         const int j = g0 + lane;
         bool touch = false;
         if (j < cnt && lo + j < warp_last) {
-          const float4 q0 = st[j].q0;
-          const float2 q1 = *reinterpret_cast<const float2*>(&st[j].q1);
-          const float twoL = st[j].q2.z;
-          touch = gcr_subrect_touch(q0.x, q0.y, q0.z, q0.w, q1.x, twoL, rx0, rx1, ry0, ry1);
+          const float4 q0 = st[j].q0;   // x, y, A, B
+          const float4 q1 = st[j].q1;   // C, o, 2 ln(255 o), -
+          touch = gcr_subrect_touch(q0.x, q0.y, q0.z, q0.w, q1.x, q1.z, rx0, rx1, ry0, ry1);
         }
         unsigned mask = __ballot_sync(0xffffffffu, touch);
         while (mask) {
@@ -224,8 +246,8 @@ blend_bwd_kernel(GcrBlendArgs a) {
           mask &= ~(1u << bit);
           const int jj = g0 + bit;
           const float4 r0 = st[jj].q0;
-          const float4 r1 = st[jj].q1;
-          const float cb = st[jj].q2.x;
+          const float2 r1 = *reinterpret_cast<const float2*>(&st[jj].q1);   // C, o
+          const float4 col = st[jj].q2;                                     // r, g, b, -
           // straight-line evaluation (the warp is issue-bound: no per-test branches); the
           // per-pixel recurrences are only committed on contributing lanes
           const float dx = __fsub_rn(r0.x, pxf);
@@ -248,10 +270,10 @@ blend_bwd_kernel(GcrBlendArgs a) {
             acc0 = fmaf(last_alpha, lc0, one_m_la * acc0);
             acc1 = fmaf(last_alpha, lc1, one_m_la * acc1);
             acc2 = fmaf(last_alpha, lc2, one_m_la * acc2);
-            lc0 = r1.z; lc1 = r1.w; lc2 = cb;
-            float dL_dalpha = (r1.z - acc0) * dLp0;
-            dL_dalpha = fmaf(r1.w - acc1, dLp1, dL_dalpha);
-            dL_dalpha = fmaf(cb - acc2, dLp2, dL_dalpha);
+            lc0 = col.x; lc1 = col.y; lc2 = col.z;
+            float dL_dalpha = (col.x - acc0) * dLp0;
+            dL_dalpha = fmaf(col.y - acc1, dLp1, dL_dalpha);
+            dL_dalpha = fmaf(col.z - acc2, dLp2, dL_dalpha);
             last_alpha = alpha;
             wB = fmaf(dL_dalpha, T, (-T_final * inv_1ma) * bg_dot_dpixel);
             wA = alpha * T;
@@ -271,6 +293,7 @@ blend_bwd_kernel(GcrBlendArgs a) {
       }
     }
     if (nslot > 0) flush(nslot);   // stage s is recycled after this batch's barrier
+    stage_id[s ^ 1][tid] = fetched_tag;   // nobody reads side s^1 during this batch
     __syncthreads();
   }
 }

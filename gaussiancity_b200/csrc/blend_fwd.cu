@@ -87,10 +87,9 @@ blend_fwd_kernel(GcrBlendArgs a) {
         const int j = g0 + lane;
         bool touch = false;
         if (j < cnt) {
-          const float4 q0 = st[j].q0;
-          const float2 q1 = *reinterpret_cast<const float2*>(&st[j].q1);
-          const float twoL = st[j].q2.z;
-          touch = gcr_subrect_touch(q0.x, q0.y, q0.z, q0.w, q1.x, twoL, rx0, rx1, ry0, ry1);
+          const float4 q0 = st[j].q0;   // x, y, A, B
+          const float4 q1 = st[j].q1;   // C, o, 2 ln(255 o), -
+          touch = gcr_subrect_touch(q0.x, q0.y, q0.z, q0.w, q1.x, q1.z, rx0, rx1, ry0, ry1);
         }
         unsigned mask = __ballot_sync(0xffffffffu, touch);
         const GcrRecord* __restrict__ stc = st + g0;        // chunk-invariant parts hoisted
@@ -100,7 +99,7 @@ blend_fwd_kernel(GcrBlendArgs a) {
           mask &= mask - 1;
           const GcrRecord* __restrict__ rec = stc + bit;
           const float4 r0 = rec->q0;   // x, y, A, B   (broadcast LDS.128)
-          const float4 r1 = rec->q1;   // C, o, r, g
+          const float2 r1 = *reinterpret_cast<const float2*>(&rec->q1);   // C, o
           // straight-line evaluation, state updates predicated: same arithmetic as the reference
           // on every contributing lane, no per-test branches (the warp is issue-bound)
           const float dx = __fsub_rn(r0.x, pxf);
@@ -112,10 +111,10 @@ blend_fwd_kernel(GcrBlendArgs a) {
           const bool sat = ok && (test_T < 0.0001f);
           done = done || sat;
           if (ok && !sat) {
-            const float cb = rec->q2.x;  // b
-            C0 = __fmaf_rn(T, __fmul_rn(alpha, r1.z), C0);
-            C1 = __fmaf_rn(T, __fmul_rn(alpha, r1.w), C1);
-            C2 = __fmaf_rn(T, __fmul_rn(alpha, cb), C2);
+            const float4 c = rec->q2;    // r, g, b, -
+            C0 = __fmaf_rn(T, __fmul_rn(alpha, c.x), C0);
+            C1 = __fmaf_rn(T, __fmul_rn(alpha, c.y), C1);
+            C2 = __fmaf_rn(T, __fmul_rn(alpha, c.z), C2);
             T = test_T;
             last_contributor = pos1 + (uint32_t)bit;
           }

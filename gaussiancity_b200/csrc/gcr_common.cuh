@@ -16,8 +16,8 @@
 // Per-Gaussian / per-instance record: 48 B = 3 x float4, 16 B aligned so one tile's slice
 // of the instance array can be moved into shared memory with a single TMA bulk copy.
 //   q0 = { mean2D.x, mean2D.y, conic.x (A), conic.y (B) }
-//   q1 = { conic.z (C), opacity, r, g }
-//   q2 = { b, bits(gaussian index), 2*ln(255*opacity) (cull threshold), unused }
+//   q1 = { conic.z (C), opacity, 2*ln(255*opacity) (cull threshold), unused }     <- projection
+//   q2 = { r, g, b, unused }                                                      <- colour stage
 // ---------------------------------------------------------------------------------------
 struct __align__(16) GcrRecord {
   float4 q0, q1, q2;

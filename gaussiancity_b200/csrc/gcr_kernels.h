@@ -45,19 +45,27 @@ struct GcrPreprocessArgs {
   uint8_t* clamped;
   uint8_t* owner;           // rank whose stripe holds the centre row (GCR_NO_OWNER if culled)
   unsigned long long* total_tiles;  // zeroed; += sum of tiles_touched (= num_rendered)
+  // balanced stripes (deferred mode) / standalone partition
+  unsigned long long* packed_rects;  // [P] global rect + centre row, 0 = culled
+  uint32_t* row_hist;                // [grid_y + 1] zeroed: instances per tile row, +1 = done-CTA ticket
+  int* stripe_bounds_out;            // [shard_count + 1]
   float* dbg_cov3D;  // optional [P,6]
 };
 
-cudaError_t gcr_launch_preprocess_fwd(const GcrPreprocessArgs& a, cudaStream_t stream);
+// Forward preprocessing.  deferred == false: one kernel (projection + colour of the rendered
+// Gaussians).  deferred == true (balanced stripes): projection of every Gaussian + row histogram
+// + stripe cut, then gcr_launch_stripe_select: owner / clipped rect / colours of this stripe's
+// Gaussians.
+cudaError_t gcr_launch_project(const GcrPreprocessArgs& a, bool deferred, cudaStream_t stream);
+cudaError_t gcr_launch_stripe_select(const GcrPreprocessArgs& a, cudaStream_t stream);
 cudaError_t gcr_launch_check_frustum(int P, const float* means3D, const float* viewmatrix, bool* present,
                                      cudaStream_t stream);
 
-// Balanced tile-row stripes: a geometry-only pass over all Gaussians (44 B
-// each: no colour) accumulates the number of tile instances per tile row; the last CTA cuts the
-// rows into `shard_count` contiguous stripes of about equal instance count and writes
-// bounds[0..shard_count] (device).  `row_hist` is grid_y + 1 zeroed words (+1 = done-CTA ticket).
-cudaError_t gcr_launch_stripe_partition(const GcrPreprocessArgs& a, uint32_t* row_hist, int* bounds_out,
-                                        cudaStream_t stream);
+// Balanced tile-row stripes as a standalone pass: a geometry-only sweep over all
+// Gaussians (44 B each: no colour) accumulates the number of tile instances per tile row; the last
+// CTA cuts the rows into `shard_count` contiguous stripes of about equal instance count and writes
+// a.stripe_bounds_out[0..shard_count] (device).  a.row_hist is grid_y + 1 zeroed words.
+cudaError_t gcr_launch_stripe_partition(const GcrPreprocessArgs& a, cudaStream_t stream);
 
 // ---- sort / emit / ranges (binning.cu) --------------------------------------------------------
 // Stable LSD radix sort of (key,value) u32 pairs on key bits [0, end_bit): ceil(end_bit/8)
@@ -108,6 +116,7 @@ struct GcrBlendArgs {
   const uint2* ranges;
   const uint32_t* point_list;  // sorted instance -> Gaussian index
   const GcrRecord* records;    // per-Gaussian records, gathered through point_list
+  const uint8_t* owner;        // per-Gaussian owner rank (backward with n_acc > 1)
   const float* bg;  // [3]
   float* final_T;          // [H*W]
   uint32_t* n_contrib;     // [H*W]

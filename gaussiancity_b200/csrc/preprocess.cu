@@ -157,202 +157,353 @@ __forceinline__ __device__ bool gcr_project(const GcrPreprocessArgs& a, int idx,
   return (o.rmax.x - o.rmin.x) * (o.rmax.y - o.rmin.y) != 0;
 }
 
-// rank whose stripe [bounds[r], bounds[r+1]) holds the Gaussian's centre tile row, clamped into
-// the rows its rect touches (the centre row always is one of them: radius >= 1)
-__forceinline__ __device__ int gcr_owner_rank(const GcrPreprocessArgs& a, const GcrProjected& g) {
-  if (a.stripe_bounds == nullptr) return 0;
+// ---- stripes ------------------------------------------------------------------------------------
+// A Gaussian's global tile rect and centre tile row in one 64-bit word (12 bits each: images up to
+// 65 536 px a side), 0 = culled: what the stripe selection needs once the bounds are known.
+__forceinline__ __device__ unsigned long long pack_rect(const GcrProjected& g) {
+  // centre row, clamped into the rows the rect touches (it always is one of them: radius >= 1)
   int cr = (int)floorf(g.pix_y * (1.0f / GCR_TILE_Y));
   cr = min(max(cr, (int)g.rmin.y), (int)g.rmax.y - 1);
-  int owner = 0;
-  for (int r = 1; r < a.shard_count; ++r)
-    if (cr >= a.stripe_bounds[r]) owner = r;
-  return owner;
+  return (unsigned long long)g.rmin.x | ((unsigned long long)g.rmax.x << 12) |
+         ((unsigned long long)g.rmin.y << 24) | ((unsigned long long)g.rmax.y << 36) |
+         ((unsigned long long)cr << 48) | (1ull << 63);
 }
 
-template <bool kHasSH>
-__forceinline__ __device__ uint32_t preprocess_one(const GcrPreprocessArgs& a, const int idx) {
-  // Defaults for culled Gaussians.
-  int radius_out = 0;
-  uint32_t tiles = 0;
-  uint32_t depth_key = 0xFFFFFFFFu;  // dropped by the first pass of the depth sort
-  uint8_t owner_out = GCR_NO_OWNER;
+// What one rank makes of a visible Gaussian once the stripe bounds are known: the owner (rank
+// whose stripe [bounds[r], bounds[r+1]) holds the centre row), the rect clipped to this rank's
+// stripe in the form the emit stage reads (x0 | y0 << 16, width | rows << 16) and its tile count.
+struct StripeSelect {
+  uint32_t tiles;
+  uint2 rect;
+  uint8_t owner;
+};
+__forceinline__ __device__ StripeSelect stripe_select(unsigned long long packed, const int* __restrict__ bounds,
+                                                      int rank, int count, int grid_y) {
+  const uint32_t x0 = (uint32_t)(packed & 0xFFFu), x1 = (uint32_t)((packed >> 12) & 0xFFFu);
+  const int ry0 = (int)((packed >> 24) & 0xFFFu), ry1 = (int)((packed >> 36) & 0xFFFu);
+  const int cr = (int)((packed >> 48) & 0xFFFu);
+  int row0 = 0, row1 = grid_y, owner = 0;
+  if (bounds != nullptr) {
+    row0 = bounds[rank];
+    row1 = bounds[rank + 1];
+    for (int r = 1; r < count; ++r)
+      if (cr >= bounds[r]) owner = r;
+  }
+  const int y0 = max(ry0, row0), y1 = min(ry1, row1);
+  StripeSelect o;
+  o.owner = (uint8_t)owner;
+  o.tiles = y1 > y0 ? (x1 - x0) * (uint32_t)(y1 - y0) : 0u;
+  o.rect = make_uint2(x0 | ((uint32_t)y0 << 16), (x1 - x0) | ((uint32_t)(y1 - y0) << 16));
+  return o;
+}
 
-  const float px = a.means3D[3 * idx + 0];
-  const float py = a.means3D[3 * idx + 1];
-  const float pz = a.means3D[3 * idx + 2];
-
-  GcrProjected g;
-  if (gcr_project(a, idx, px, py, pz, g)) {
-    radius_out = g.radius;
-    const int owner = gcr_owner_rank(a, g);
-    owner_out = (uint8_t)owner;
-    // rows of the rect inside this rank's stripe (all of them without sharding)
-    int row0 = 0, row1 = a.grid_y;
-    if (a.stripe_bounds != nullptr) {
-      row0 = a.stripe_bounds[a.shard_rank];
-      row1 = a.stripe_bounds[a.shard_rank + 1];
-    }
-    const int y0 = max((int)g.rmin.y, row0), y1 = min((int)g.rmax.y, row1);
-    if (y1 > y0) {
-      tiles = (g.rmax.x - g.rmin.x) * (uint32_t)(y1 - y0);
-      // the emit stage needs only this word per Gaussian: x0 | y0 << 16, width | rows << 16
-      a.rects[idx] = make_uint2(g.rmin.x | ((uint32_t)y0 << 16), (g.rmax.x - g.rmin.x) | ((uint32_t)(y1 - y0) << 16));
-      {
-        // colour: SH evaluation (forward.cu:20-66) or precomputed
-        float cr, cg, cb;
-        if (kHasSH) {
-          const float dx = __fsub_rn(px, a.campos[0]);
-          const float dy = __fsub_rn(py, a.campos[1]);
-          const float dz = __fsub_rn(pz, a.campos[2]);
-          const float len = sqrtf(dot3(dx, dx, dy, dy, dz, dz));
-          const float x = dx / len, y = dy / len, z = dz / len;
-          const float4* __restrict__ sh4 =
-              reinterpret_cast<const float4*>(a.shs + (size_t)idx * a.M * 3);
-          // coefficients are read as float4 (M*3 floats = 3M/4 float4 when M in {1,4,9,16}:
-          // M=1 -> 3 floats (not a float4 multiple) so fall back to scalar loads there).
-          float sh[48];
-          const int nfl = a.M * 3;
-          if ((nfl & 7) == 0) {
-            const float* __restrict__ shp = a.shs + (size_t)idx * a.M * 3;
+// SH colour of one Gaussian (computeColorFromSH, forward.cu:20-66): rgb clamped at 0, returns
+// the clamp flags (bit ch set when channel ch was negative before the clamp).
+__forceinline__ __device__ uint8_t gcr_sh_colour(const GcrPreprocessArgs& a, const int idx, const float px,
+                                                  const float py, const float pz, float& cr, float& cg,
+                                                  float& cb) {
+    const float dx = __fsub_rn(px, a.campos[0]);
+    const float dy = __fsub_rn(py, a.campos[1]);
+    const float dz = __fsub_rn(pz, a.campos[2]);
+    const float len = sqrtf(dot3(dx, dx, dy, dy, dz, dz));
+    const float x = dx / len, y = dy / len, z = dz / len;
+    const float4* __restrict__ sh4 =
+        reinterpret_cast<const float4*>(a.shs + (size_t)idx * a.M * 3);
+    // coefficients are read as float4 (M*3 floats = 3M/4 float4 when M in {1,4,9,16}:
+    // M=1 -> 3 floats (not a float4 multiple) so fall back to scalar loads there).
+    float sh[48];
+    const int nfl = a.M * 3;
+    if ((nfl & 7) == 0) {
+      const float* __restrict__ shp = a.shs + (size_t)idx * a.M * 3;
 #pragma unroll
-            for (int k = 0; k < 6; ++k) {
-              if (k * 8 < nfl) {
-                float v[8];
-                gcr_ldg_nc_v8(shp + 8 * k, v);
+      for (int k = 0; k < 6; ++k) {
+        if (k * 8 < nfl) {
+          float v[8];
+          gcr_ldg_nc_v8(shp + 8 * k, v);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) sh[8 * k + i] = v[i];
-              }
-            }
-          } else if ((nfl & 3) == 0) {
-#pragma unroll
-            for (int k = 0; k < 12; ++k) {
-              if (k * 4 < nfl) {
-                const float4 v = __ldg(sh4 + k);
-                sh[4 * k + 0] = v.x; sh[4 * k + 1] = v.y; sh[4 * k + 2] = v.z; sh[4 * k + 3] = v.w;
-              }
-            }
-          } else {
-            const float* __restrict__ shf = a.shs + (size_t)idx * a.M * 3;
-#pragma unroll
-            for (int k = 0; k < 48; ++k)
-              if (k < nfl) sh[k] = __ldg(shf + k);
-          }
-#define SHC(k, ch) sh[3 * (k) + (ch)]
-          // Basis scalars and the accumulation chain are pinned to the contraction nvcc emits for
-          // the reference's glm::vec3 expression (decoded from its SASS, forward.cu:20-66): every
-          // basis scalar is built with plain mul/add except 3xx-yy, 4zz-xx, 2zz-3xx-3yy, xx-3yy
-          // (fma), then res = fma(scalar, sh[k], res) in coefficient order.
-          float s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f, s5 = 0.f, s6 = 0.f, s7 = 0.f, s8 = 0.f;
-          float s9 = 0.f, s10 = 0.f, s11 = 0.f, s12 = 0.f, s13 = 0.f, s14 = 0.f, s15 = 0.f;
-          if (a.D > 0) {
-            s1 = __fmul_rn(y, GCR_SH_C1);
-            s2 = __fmul_rn(z, GCR_SH_C1);
-            s3 = __fmul_rn(x, GCR_SH_C1);
-            if (a.D > 1) {
-              const float xy = __fmul_rn(y, x), zy = __fmul_rn(z, y), zx = __fmul_rn(z, x);
-              const float zz = __fmul_rn(z, z), xx = __fmul_rn(x, x), yy = __fmul_rn(y, y);
-              const float zz2 = __fadd_rn(zz, zz);
-              const float xx_yy = __fsub_rn(xx, yy);
-              s4 = __fmul_rn(xy, GCR_SH_C2[0]);
-              s5 = __fmul_rn(zy, GCR_SH_C2[1]);
-              s6 = __fmul_rn(__fsub_rn(__fsub_rn(zz2, xx), yy), GCR_SH_C2[2]);
-              s7 = __fmul_rn(zx, GCR_SH_C2[3]);
-              s8 = __fmul_rn(xx_yy, GCR_SH_C2[4]);
-              if (a.D > 2) {
-                const float q = __fsub_rn(__fmaf_rn(zz, 4.0f, -xx), yy);                 // 4zz - xx - yy
-                const float u = __fmaf_rn(yy, -3.0f, __fmaf_rn(xx, -3.0f, zz2));          // 2zz - 3xx - 3yy
-                s9 = __fmul_rn(__fmul_rn(y, GCR_SH_C3[0]), __fmaf_rn(xx, 3.0f, -yy));
-                s10 = __fmul_rn(__fmul_rn(xy, GCR_SH_C3[1]), z);
-                s11 = __fmul_rn(__fmul_rn(y, GCR_SH_C3[2]), q);
-                s12 = __fmul_rn(__fmul_rn(z, GCR_SH_C3[3]), u);
-                s13 = __fmul_rn(q, __fmul_rn(x, GCR_SH_C3[4]));
-                s14 = __fmul_rn(xx_yy, __fmul_rn(z, GCR_SH_C3[5]));
-                s15 = __fmul_rn(__fmul_rn(x, GCR_SH_C3[6]), __fmaf_rn(yy, -3.0f, xx));
-              }
-            }
-          }
-          float res[3];
-#pragma unroll
-          for (int ch = 0; ch < 3; ++ch) {
-            float v = __fmul_rn(GCR_SH_C0, SHC(0, ch));
-            if (a.D > 0) {
-              v = __fmaf_rn(-s1, SHC(1, ch), v);
-              v = __fmaf_rn(s2, SHC(2, ch), v);
-              v = __fmaf_rn(-s3, SHC(3, ch), v);
-              if (a.D > 1) {
-                v = __fmaf_rn(s4, SHC(4, ch), v);
-                v = __fmaf_rn(s5, SHC(5, ch), v);
-                v = __fmaf_rn(s6, SHC(6, ch), v);
-                v = __fmaf_rn(s7, SHC(7, ch), v);
-                v = __fmaf_rn(s8, SHC(8, ch), v);
-                if (a.D > 2) {
-                  v = __fmaf_rn(s9, SHC(9, ch), v);
-                  v = __fmaf_rn(s10, SHC(10, ch), v);
-                  v = __fmaf_rn(s11, SHC(11, ch), v);
-                  v = __fmaf_rn(s12, SHC(12, ch), v);
-                  v = __fmaf_rn(s13, SHC(13, ch), v);
-                  v = __fmaf_rn(s14, SHC(14, ch), v);
-                  v = __fmaf_rn(s15, SHC(15, ch), v);
-                }
-              }
-            }
-            res[ch] = __fadd_rn(v, 0.5f);
-          }
-#undef SHC
-          const uint8_t cl = (res[0] < 0 ? 1 : 0) | (res[1] < 0 ? 2 : 0) | (res[2] < 0 ? 4 : 0);
-          a.clamped[idx] = cl;
-          cr = fmaxf(res[0], 0.0f);
-          cg = fmaxf(res[1], 0.0f);
-          cb = fmaxf(res[2], 0.0f);
-        } else {
-          cr = a.colors_precomp[3 * idx + 0];
-          cg = a.colors_precomp[3 * idx + 1];
-          cb = a.colors_precomp[3 * idx + 2];
+          for (int i = 0; i < 8; ++i) sh[8 * k + i] = v[i];
         }
-
-        const float opacity = a.opacities[idx];
-        GcrRecord rec;
-        rec.q0 = make_float4(g.pix_x, g.pix_y, g.conic_x, g.conic_y);
-        rec.q1 = make_float4(g.conic_z, opacity, cr, cg);
-        // cull threshold 2*ln(255*opacity): a pixel can only reach alpha >= 1/255 when
-        // A dx^2 + 2B dx dy + C dy^2 <= this value (used with a safety margin, blend_*.cu).
-        rec.q2 = make_float4(cb, __uint_as_float((uint32_t)idx), 2.0f * logf(255.0f * opacity),
-                             __uint_as_float((uint32_t)owner));
-        a.records[idx] = rec;
-        depth_key = __float_as_uint(g.vz);
+      }
+    } else if ((nfl & 3) == 0) {
+#pragma unroll
+      for (int k = 0; k < 12; ++k) {
+        if (k * 4 < nfl) {
+          const float4 v = __ldg(sh4 + k);
+          sh[4 * k + 0] = v.x; sh[4 * k + 1] = v.y; sh[4 * k + 2] = v.z; sh[4 * k + 3] = v.w;
+        }
+      }
+    } else {
+      const float* __restrict__ shf = a.shs + (size_t)idx * a.M * 3;
+#pragma unroll
+      for (int k = 0; k < 48; ++k)
+        if (k < nfl) sh[k] = __ldg(shf + k);
+    }
+#define SHC(k, ch) sh[3 * (k) + (ch)]
+    // Basis scalars and the accumulation chain are pinned to the contraction nvcc emits for
+    // the reference's glm::vec3 expression (decoded from its SASS, forward.cu:20-66): every
+    // basis scalar is built with plain mul/add except 3xx-yy, 4zz-xx, 2zz-3xx-3yy, xx-3yy
+    // (fma), then res = fma(scalar, sh[k], res) in coefficient order.
+    float s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f, s5 = 0.f, s6 = 0.f, s7 = 0.f, s8 = 0.f;
+    float s9 = 0.f, s10 = 0.f, s11 = 0.f, s12 = 0.f, s13 = 0.f, s14 = 0.f, s15 = 0.f;
+    if (a.D > 0) {
+      s1 = __fmul_rn(y, GCR_SH_C1);
+      s2 = __fmul_rn(z, GCR_SH_C1);
+      s3 = __fmul_rn(x, GCR_SH_C1);
+      if (a.D > 1) {
+        const float xy = __fmul_rn(y, x), zy = __fmul_rn(z, y), zx = __fmul_rn(z, x);
+        const float zz = __fmul_rn(z, z), xx = __fmul_rn(x, x), yy = __fmul_rn(y, y);
+        const float zz2 = __fadd_rn(zz, zz);
+        const float xx_yy = __fsub_rn(xx, yy);
+        s4 = __fmul_rn(xy, GCR_SH_C2[0]);
+        s5 = __fmul_rn(zy, GCR_SH_C2[1]);
+        s6 = __fmul_rn(__fsub_rn(__fsub_rn(zz2, xx), yy), GCR_SH_C2[2]);
+        s7 = __fmul_rn(zx, GCR_SH_C2[3]);
+        s8 = __fmul_rn(xx_yy, GCR_SH_C2[4]);
+        if (a.D > 2) {
+          const float q = __fsub_rn(__fmaf_rn(zz, 4.0f, -xx), yy);                 // 4zz - xx - yy
+          const float u = __fmaf_rn(yy, -3.0f, __fmaf_rn(xx, -3.0f, zz2));          // 2zz - 3xx - 3yy
+          s9 = __fmul_rn(__fmul_rn(y, GCR_SH_C3[0]), __fmaf_rn(xx, 3.0f, -yy));
+          s10 = __fmul_rn(__fmul_rn(xy, GCR_SH_C3[1]), z);
+          s11 = __fmul_rn(__fmul_rn(y, GCR_SH_C3[2]), q);
+          s12 = __fmul_rn(__fmul_rn(z, GCR_SH_C3[3]), u);
+          s13 = __fmul_rn(q, __fmul_rn(x, GCR_SH_C3[4]));
+          s14 = __fmul_rn(xx_yy, __fmul_rn(z, GCR_SH_C3[5]));
+          s15 = __fmul_rn(__fmul_rn(x, GCR_SH_C3[6]), __fmaf_rn(yy, -3.0f, xx));
+        }
       }
     }
-  }
-  a.radii[idx] = radius_out;
-  a.tiles_touched[idx] = tiles;
-  a.depth_keys[idx] = depth_key;
-  a.owner[idx] = owner_out;
-  return tiles;
+    float res[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      float v = __fmul_rn(GCR_SH_C0, SHC(0, ch));
+      if (a.D > 0) {
+        v = __fmaf_rn(-s1, SHC(1, ch), v);
+        v = __fmaf_rn(s2, SHC(2, ch), v);
+        v = __fmaf_rn(-s3, SHC(3, ch), v);
+        if (a.D > 1) {
+          v = __fmaf_rn(s4, SHC(4, ch), v);
+          v = __fmaf_rn(s5, SHC(5, ch), v);
+          v = __fmaf_rn(s6, SHC(6, ch), v);
+          v = __fmaf_rn(s7, SHC(7, ch), v);
+          v = __fmaf_rn(s8, SHC(8, ch), v);
+          if (a.D > 2) {
+            v = __fmaf_rn(s9, SHC(9, ch), v);
+            v = __fmaf_rn(s10, SHC(10, ch), v);
+            v = __fmaf_rn(s11, SHC(11, ch), v);
+            v = __fmaf_rn(s12, SHC(12, ch), v);
+            v = __fmaf_rn(s13, SHC(13, ch), v);
+            v = __fmaf_rn(s14, SHC(14, ch), v);
+            v = __fmaf_rn(s15, SHC(15, ch), v);
+          }
+        }
+      }
+      res[ch] = __fadd_rn(v, 0.5f);
+    }
+#undef SHC
+    const uint8_t cl = (res[0] < 0 ? 1 : 0) | (res[1] < 0 ? 2 : 0) | (res[2] < 0 ? 4 : 0);
+    cr = fmaxf(res[0], 0.0f);
+    cg = fmaxf(res[1], 0.0f);
+    cb = fmaxf(res[2], 0.0f);
+  return cl;
 }
 
-template <bool kHasSH>
-__global__ void __launch_bounds__(256, 3)   // <= 85 registers: 3 CTAs/SM for this streaming kernel
-preprocess_fwd_kernel(GcrPreprocessArgs a) {
-  __shared__ uint32_t s_sum;
-  if (threadIdx.x == 0) s_sum = 0;
-  __syncthreads();
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t tiles = 0;
-  if (idx < a.P) tiles = preprocess_one<kHasSH>(a, idx);
-  // num_rendered = sum of the tile counts: one reduction per CTA, so the host can size the
-  // binning buffer while the depth sort is still running (api.cu)
-  const uint32_t wsum = __reduce_add_sync(0xffffffffu, tiles);
-  if ((threadIdx.x & 31) == 0 && wsum != 0) atomicAdd(&s_sum, wsum);
-  __syncthreads();
-  if (threadIdx.x == 0 && s_sum != 0) atomicAdd(a.total_tiles, (unsigned long long)s_sum);
-}
-
-// Stripe partition pre-pass: per tile row, the number of tile instances (rect width summed over
-// the Gaussians whose rect covers the row); the last CTA to finish cuts the rows into
-// shard_count contiguous stripes of about equal instance count.
+// ---- kernel 1: projection -----------------------------------------------------------------------
+// One thread per Gaussian, geometry only (44 B read; the colour comes later and only for the
+// Gaussians that are rendered).  Writes radii, the depth key, the geometry half of the record
+// and -- on the colors_precomp path -- its colour.
+//   kDeferred == false: the stripe (if any) is known: tiles_touched / clipped rect / owner are
+//     finished here and the CTA adds its tile count to num_rendered.
+//   kDeferred == true : balanced stripes are wanted and can only be cut once every Gaussian's
+//     rect is known: the kernel stores the packed global rect, accumulates the tile-instance
+//     count of every tile row, and the LAST CTA cuts the rows into shard_count stripes of about
+//     equal instance count (deterministic: every rank computes the same bounds from the same
+//     inputs, so the ranks never have to talk).  stripe_select_kernel then finishes the job.
 constexpr int kPartRowsSmem = 1024;
+
+__device__ void cut_stripes(volatile const uint32_t* h, int grid_y, int n, int* __restrict__ bounds) {
+  unsigned long long total = 0;
+  for (int r = 0; r < grid_y; ++r) total += h[r];
+  bounds[0] = 0;
+  bounds[n] = grid_y;
+  if (total == 0) {
+    for (int k = 1; k < n; ++k) bounds[k] = (int)((long long)grid_y * k / n);
+    return;
+  }
+  // bounds[k] = the row boundary whose instance prefix is nearest to k/n of the total
+  unsigned long long prefix = 0;   // instances in rows < r
+  int r = 0;
+  for (int k = 1; k < n; ++k) {
+    const unsigned long long target = total * (unsigned long long)k / (unsigned long long)n;
+    while (r < grid_y && prefix + h[r] <= target) prefix += h[r++];
+    // boundary at r (prefix <= target) or r + 1 (prefix + h[r] > target): take the nearer
+    if (r < grid_y && (prefix + h[r] - target) < (target - prefix)) prefix += h[r++];
+    bounds[k] = r;
+  }
+}
+
+template <bool kHasSH, bool kDeferred>
+__global__ void __launch_bounds__(256, (kHasSH && !kDeferred) ? 3 : 4)
+project_kernel(GcrPreprocessArgs a) {
+  __shared__ uint32_t hist[kDeferred ? kPartRowsSmem : 1];
+  __shared__ uint32_t s_sum;
+  __shared__ bool s_last;
+  const int tid = threadIdx.x;
+  const bool use_smem = a.grid_y <= kPartRowsSmem;
+  if (tid == 0) s_sum = 0;
+  if (kDeferred && use_smem)
+    for (int r = tid; r < a.grid_y; r += blockDim.x) hist[r] = 0;
+  __syncthreads();
+  uint32_t my_tiles = 0;
+  // deferred: persistent CTAs (one row-histogram flush each); direct: one Gaussian per thread
+  const int stride = kDeferred ? (int)(gridDim.x * blockDim.x) : a.P;
+  for (int idx = blockIdx.x * blockDim.x + tid; idx < a.P; idx += stride) {
+    int radius_out = 0;
+    uint32_t depth_key = 0xFFFFFFFFu;  // dropped by the first pass of the depth sort
+    unsigned long long packed = 0ull;
+    uint32_t tiles = 0;
+    uint8_t owner_out = GCR_NO_OWNER;
+    bool want_colour = false;
+    const float px = a.means3D[3 * idx + 0];
+    const float py = a.means3D[3 * idx + 1];
+    const float pz = a.means3D[3 * idx + 2];
+    GcrProjected g;
+    if (gcr_project(a, idx, px, py, pz, g)) {
+      radius_out = g.radius;
+      packed = pack_rect(g);
+      bool rendered = true;
+      if (kDeferred) {
+        const uint32_t w = g.rmax.x - g.rmin.x;
+        for (uint32_t r = g.rmin.y; r < g.rmax.y; ++r) atomicAdd(use_smem ? &hist[r] : &a.row_hist[r], w);
+      } else {
+        const StripeSelect sel = stripe_select(packed, a.stripe_bounds, a.shard_rank, a.shard_count, a.grid_y);
+        owner_out = sel.owner;
+        tiles = sel.tiles;
+        rendered = tiles != 0;
+        if (rendered) a.rects[idx] = sel.rect;
+      }
+      if (rendered) {
+        const float opacity = a.opacities[idx];
+        GcrRecord* rec = a.records + idx;
+        rec->q0 = make_float4(g.pix_x, g.pix_y, g.conic_x, g.conic_y);
+        // cull threshold 2*ln(255*opacity): a pixel can only reach alpha >= 1/255 when
+        // A dx^2 + 2B dx dy + C dy^2 <= this value (used with a safety margin, blend_*.cu).
+        rec->q1 = make_float4(g.conic_z, opacity, 2.0f * logf(255.0f * opacity), 0.f);
+        if (!kHasSH) {
+          rec->q2 = make_float4(a.colors_precomp[3 * idx + 0], a.colors_precomp[3 * idx + 1],
+                                a.colors_precomp[3 * idx + 2], 0.f);
+        }
+        depth_key = __float_as_uint(g.vz);
+        want_colour = kHasSH && !kDeferred;
+      }
+    }
+    a.radii[idx] = radius_out;
+    a.depth_keys[idx] = depth_key;
+    if (kDeferred) {
+      a.packed_rects[idx] = packed;
+    } else {
+      a.tiles_touched[idx] = tiles;
+      a.owner[idx] = owner_out;
+      my_tiles += tiles;
+    }
+    if (want_colour) {
+      // the stripe is known, so only Gaussians that are rendered get here.  Last on purpose: the
+      // 48 coefficient registers meet as few live values as possible.
+      float cr, cg, cb;
+      a.clamped[idx] = gcr_sh_colour(a, idx, px, py, pz, cr, cg, cb);
+      a.records[idx].q2 = make_float4(cr, cg, cb, 0.f);
+    }
+  }
+  if (!kDeferred) {
+    // num_rendered = sum of the tile counts: one reduction per CTA, so the host can size the
+    // binning buffer while the depth sort is still running (api.cu)
+    const uint32_t wsum = __reduce_add_sync(0xffffffffu, my_tiles);
+    if ((tid & 31) == 0 && wsum != 0) atomicAdd(&s_sum, wsum);
+    __syncthreads();
+    if (tid == 0 && s_sum != 0) atomicAdd(a.total_tiles, (unsigned long long)s_sum);
+    return;
+  }
+  __syncthreads();
+  if (use_smem)
+    for (int r = tid; r < a.grid_y; r += blockDim.x)
+      if (hist[r] != 0) atomicAdd(&a.row_hist[r], hist[r]);
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(&a.row_hist[a.grid_y], 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last || tid != 0) return;
+  __threadfence();
+  cut_stripes(a.row_hist, a.grid_y, a.shard_count, a.stripe_bounds_out);
+}
+
+// ---- kernel 2 (balanced stripes only): finish what needed the bounds ------------------------------
+// Per Gaussian, in index order: owner, clipped rect, tile count (a few integer operations on the
+// packed rect).  Then (SH path) the Gaussians of the chunk that reach this rank's stripe -- ~1/N
+// of them -- are compacted (ballot + warp prefix) and only they load their 12*M bytes of
+// coefficients and evaluate the colour, with full warps.  Index order matters: the same
+// coefficient rows fetched in depth order run at a quarter of the bandwidth (measured, DRAM page
+// locality: profiles/r02_*).
+template <bool kHasSH>
+__global__ void __launch_bounds__(256, 3)
+stripe_select_kernel(GcrPreprocessArgs a) {
+  __shared__ uint16_t list[256];
+  __shared__ uint32_t wcount[8];
+  __shared__ uint32_t s_sum;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_sum = 0;
+  __syncthreads();
+  uint32_t my_tiles = 0;
+  const int nchunks = (a.P + 255) / 256;
+  for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {   // block-uniform trip count
+    const int base = chunk * 256;
+    const int idx = base + tid;
+    uint32_t tiles = 0;
+    if (idx < a.P) {
+      const unsigned long long packed = a.packed_rects[idx];
+      uint8_t owner_out = GCR_NO_OWNER;
+      if (packed != 0ull) {
+        const StripeSelect sel = stripe_select(packed, a.stripe_bounds, a.shard_rank, a.shard_count, a.grid_y);
+        owner_out = sel.owner;
+        tiles = sel.tiles;
+        if (tiles != 0) a.rects[idx] = sel.rect;
+        else a.depth_keys[idx] = 0xFFFFFFFFu;   // visible, but not in this rank's stripe
+      }
+      a.tiles_touched[idx] = tiles;
+      a.owner[idx] = owner_out;
+      my_tiles += tiles;
+    }
+    if (kHasSH) {
+      const bool need = tiles != 0;
+      const unsigned bal = __ballot_sync(0xffffffffu, need);
+      if (lane == 0) wcount[warp] = __popc(bal);
+      __syncthreads();
+      uint32_t before = 0, count = 0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        const uint32_t c = wcount[w];
+        if (w < warp) before += c;
+        count += c;
+      }
+      if (need) list[before + __popc(bal & ((1u << lane) - 1))] = (uint16_t)tid;
+      __syncthreads();
+      if ((uint32_t)tid < count) {
+        const int g = base + (int)list[tid];
+        float cr, cg, cb;
+        a.clamped[g] = gcr_sh_colour(a, g, a.means3D[3 * g + 0], a.means3D[3 * g + 1], a.means3D[3 * g + 2],
+                                     cr, cg, cb);
+        a.records[g].q2 = make_float4(cr, cg, cb, 0.f);
+      }
+      // list / wcount are rewritten only after the next chunk's first barrier
+    }
+  }
+  const uint32_t wsum = __reduce_add_sync(0xffffffffu, my_tiles);
+  if (lane == 0 && wsum != 0) atomicAdd(&s_sum, wsum);
+  __syncthreads();
+  if (tid == 0 && s_sum != 0) atomicAdd(a.total_tiles, (unsigned long long)s_sum);
+}
+
+// Standalone partition (gcr_stripe_partition): the same row histogram + cut, nothing else written.
 __global__ void __launch_bounds__(256)
-stripe_partition_kernel(GcrPreprocessArgs a, uint32_t* __restrict__ row_hist, int* __restrict__ bounds) {
+stripe_partition_kernel(GcrPreprocessArgs a) {
   __shared__ uint32_t hist[kPartRowsSmem];
   __shared__ bool s_last;
   const bool use_smem = a.grid_y <= kPartRowsSmem;
@@ -366,39 +517,20 @@ stripe_partition_kernel(GcrPreprocessArgs a, uint32_t* __restrict__ row_hist, in
     GcrProjected g;
     if (gcr_project(a, idx, px, py, pz, g)) {
       const uint32_t w = g.rmax.x - g.rmin.x;
-      for (uint32_t r = g.rmin.y; r < g.rmax.y; ++r) atomicAdd(use_smem ? &hist[r] : &row_hist[r], w);
+      for (uint32_t r = g.rmin.y; r < g.rmax.y; ++r) atomicAdd(use_smem ? &hist[r] : &a.row_hist[r], w);
     }
   }
   __syncthreads();
   if (use_smem)
     for (int r = threadIdx.x; r < a.grid_y; r += blockDim.x)
-      if (hist[r] != 0) atomicAdd(&row_hist[r], hist[r]);
+      if (hist[r] != 0) atomicAdd(&a.row_hist[r], hist[r]);
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(&row_hist[a.grid_y], 1u) == gridDim.x - 1;
+  if (threadIdx.x == 0) s_last = atomicAdd(&a.row_hist[a.grid_y], 1u) == gridDim.x - 1;
   __syncthreads();
   if (!s_last || threadIdx.x != 0) return;
   __threadfence();
-  volatile uint32_t* h = row_hist;
-  unsigned long long total = 0;
-  for (int r = 0; r < a.grid_y; ++r) total += h[r];
-  const int n = a.shard_count;
-  bounds[0] = 0;
-  bounds[n] = a.grid_y;
-  if (total == 0) {
-    for (int k = 1; k < n; ++k) bounds[k] = (int)((long long)a.grid_y * k / n);
-    return;
-  }
-  // bounds[k] = the row boundary whose instance prefix is nearest to k/n of the total
-  unsigned long long prefix = 0;   // instances in rows < r
-  int r = 0;
-  for (int k = 1; k < n; ++k) {
-    const unsigned long long target = total * (unsigned long long)k / (unsigned long long)n;
-    while (r < a.grid_y && prefix + h[r] <= target) prefix += h[r++];
-    // boundary at r (prefix <= target) or r + 1 (prefix + h[r] > target): take the nearer
-    if (r < a.grid_y && (prefix + h[r] - target) < (target - prefix)) prefix += h[r++];
-    bounds[k] = r;
-  }
+  cut_stripes(a.row_hist, a.grid_y, a.shard_count, a.stripe_bounds_out);
 }
 
 // mark_visible (rasterizer_impl.cu:52-62): z_view > 0.2
@@ -413,21 +545,37 @@ __global__ void check_frustum_kernel(int P, const float* __restrict__ means3D,
 
 }  // namespace
 
-cudaError_t gcr_launch_preprocess_fwd(const GcrPreprocessArgs& a, cudaStream_t stream) {
+namespace {
+inline unsigned persistent_grid(int n, int per_sm) {
+  const int blocks = (n + 255) / 256;
+  return (unsigned)(blocks < 148 * per_sm ? blocks : 148 * per_sm);
+}
+}  // namespace
+
+cudaError_t gcr_launch_project(const GcrPreprocessArgs& a, bool deferred, cudaStream_t stream) {
   if (a.P <= 0) return cudaSuccess;
-  const int blocks = (a.P + 255) / 256;
-  if (a.colors_precomp == nullptr)
-    preprocess_fwd_kernel<true><<<blocks, 256, 0, stream>>>(a);
-  else
-    preprocess_fwd_kernel<false><<<blocks, 256, 0, stream>>>(a);
+  const bool sh = a.colors_precomp == nullptr;
+  const unsigned grid = deferred ? persistent_grid(a.P, 8) : (unsigned)((a.P + 255) / 256);
+  if (deferred) {
+    if (sh) project_kernel<true, true><<<grid, 256, 0, stream>>>(a);
+    else project_kernel<false, true><<<grid, 256, 0, stream>>>(a);
+  } else {
+    if (sh) project_kernel<true, false><<<grid, 256, 0, stream>>>(a);
+    else project_kernel<false, false><<<grid, 256, 0, stream>>>(a);
+  }
   return cudaGetLastError();
 }
 
-cudaError_t gcr_launch_stripe_partition(const GcrPreprocessArgs& a, uint32_t* row_hist, int* bounds_out,
-                                        cudaStream_t stream) {
+cudaError_t gcr_launch_stripe_select(const GcrPreprocessArgs& a, cudaStream_t stream) {
   if (a.P <= 0) return cudaSuccess;
-  const int blocks = (a.P + 255) / 256;
-  stripe_partition_kernel<<<blocks < 148 * 8 ? blocks : 148 * 8, 256, 0, stream>>>(a, row_hist, bounds_out);
+  if (a.colors_precomp == nullptr) stripe_select_kernel<true><<<persistent_grid(a.P, 3 * 4), 256, 0, stream>>>(a);
+  else stripe_select_kernel<false><<<persistent_grid(a.P, 8), 256, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t gcr_launch_stripe_partition(const GcrPreprocessArgs& a, cudaStream_t stream) {
+  if (a.P <= 0) return cudaSuccess;
+  stripe_partition_kernel<<<persistent_grid(a.P, 8), 256, 0, stream>>>(a);
   return cudaGetLastError();
 }
 

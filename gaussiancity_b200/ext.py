@@ -71,12 +71,13 @@ class _Allocator:
 def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier,
                         cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height,
                         image_width, sh, degree, campos, prefiltered, debug,
-                        shard_rank=0, shard_count=1, stripe_bounds=None):
+                        shard_rank=0, shard_count=1, stripe_bounds=None, balanced=False):
     """-> (num_rendered, color[3,H,W], radii[P] int32, geomBuffer, binningBuffer, imgBuffer)
 
     shard_count > 1 renders one contiguous tile-row stripe of the frame (the rest of `color` is
-    zero); stripe_bounds: int32 CUDA tensor [shard_count + 1] (e.g. from stripe_partition), None
-    = equal-height stripes."""
+    zero); stripe_bounds: int32 CUDA tensor [shard_count + 1] (e.g. from stripe_partition); None =
+    equal-height stripes, or, with balanced=True, stripes of about equal tile-instance count cut on
+    the device during the projection pass (read them back with stripe_bounds_of)."""
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")
     if not means3D.is_cuda:
@@ -118,7 +119,8 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
                 float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp), _ptr(viewmatrix),
                 _ptr(projmatrix), _ptr(campos), float(tan_fovx), float(tan_fovy),
                 int(bool(prefiltered)), _ptr(out_color), _ptr(radii), int(bool(debug)),
-                int(shard_rank), int(shard_count), _ptr(stripe_bounds), _stream_ptr(device))
+                int(shard_rank), int(shard_count), _ptr(stripe_bounds), int(bool(balanced)),
+                _stream_ptr(device))
             rendered = _cabi.check(rc, "rasterize_gaussians")
     return rendered, out_color, radii, geom.take(), binning.take(), img.take()
 
@@ -219,6 +221,14 @@ def stripe_partition(means3D, scales, rotations, scale_modifier, viewmatrix, pro
                                       int(shard_count), _ptr(workspace), _ptr(bounds_out), _stream_ptr(device))
         _cabi.check(rc, "stripe_partition")
     return bounds_out
+
+
+def stripe_bounds_of(geomBuffer, P, shard_count):
+    """int32 [shard_count + 1]: the tile-row stripe bounds the last forward into geomBuffer used."""
+    lib = _cabi.lib()
+    off = lib.gcr_debug_offset(_cabi.GEOM_COUNTERS, int(P), 0, 16, 16) + 4 * 8
+    base = (-geomBuffer.data_ptr()) % 256
+    return geomBuffer[base + off:base + off + 4 * (int(shard_count) + 1)].view(torch.int32)
 
 
 def owner_bytes(geomBuffer, P):

@@ -5,9 +5,10 @@ per-row tile-instance counts (a geometry-only pre-pass every rank runs on the sa
 all ranks obtain the same bounds without talking).  Nothing that is per-Gaussian heavy is
 replicated: each rank
 
-  forward : projects all Gaussians (44 B each; needed to find the ones that reach its stripe),
-            but evaluates SH colours, depth-sorts, bins and blends only the ~P/world Gaussians
-            whose tile rect touches its stripe;
+  forward : projects all Gaussians (44 B each; needed to find the ones that reach its stripe --
+            the same pass counts tile instances per tile row and cuts the balanced stripes), but
+            evaluates SH colours, depth-sorts, bins and blends only the ~P/world Gaussians whose
+            tile rect touches its stripe;
   backward: blends the gradients of its own tiles.  The per-Gaussian sums of a Gaussian that
             straddles a stripe boundary have to meet somewhere: every Gaussian is OWNED by the
             rank whose stripe holds its centre row, and the blend kernel adds each record's sums
@@ -87,14 +88,14 @@ class CudaBackend:
                              self._part_ws, self._bounds)
         return self._bounds
 
-    def forward(self, inp, cam, rank, world, bounds):
+    def forward(self, inp, cam, rank, world, bounds, balanced=False):
         from . import ext
         e = torch.Tensor([])
         R, color, radii, geom, binning, img = ext.rasterize_gaussians(
             cam["bg"], inp["means3D"], inp.get("colors", e), inp["opacity"], inp["scales"],
             inp["rotations"], 1.0, e, cam["view"], cam["proj"], cam["tanfovx"], cam["tanfovy"],
             cam["img_h"], cam["img_w"], inp.get("sh", e), cam["sh_degree"], cam["campos"], False,
-            False, shard_rank=rank, shard_count=world, stripe_bounds=bounds)
+            False, shard_rank=rank, shard_count=world, stripe_bounds=bounds, balanced=balanced)
         return color, radii, dict(R=R, geom=geom, binning=binning, img=img, radii=radii)
 
     # -- exchange="collective": partial accumulators, reduced by torch.distributed ----------------
@@ -117,6 +118,10 @@ class CudaBackend:
     def owner_mask(self, state, inp, rank):
         from . import ext
         return ext.owner_bytes(state["geom"], inp["means3D"].shape[0]) == rank
+
+    def stripe_bounds(self, state, inp, world):
+        from . import ext
+        return ext.stripe_bounds_of(state["geom"], inp["means3D"].shape[0], world)
 
     # -- exchange="peer": accumulators other ranks add into over NVLink ---------------------------
     def peer_setup(self, P, rank, world, group):
@@ -234,18 +239,13 @@ class TileShardedRasterizer:
         return int(t.item())
 
     # -- one frame ---------------------------------------------------------------------------
-    def stripes(self, inp, cam):
-        if self.world == 1:
-            return None
-        if self.balanced:
-            return self.backend.partition(inp, cam, self.world)
-        return None   # the library's equal-height stripes
-
-    def render(self, inp, cam, src=0, broadcast=False, assemble=True):
+    def render(self, inp, cam, src=0, broadcast=False, assemble=True, bounds=None):
+        """bounds: explicit stripe bounds (device int32 [world + 1]); None = balanced stripes cut by
+        the forward itself (self.balanced) or equal-height ones."""
         if broadcast:
             self.broadcast_gaussians(inp, src)
-        bounds = self.stripes(inp, cam)
-        color, radii, state = self.backend.forward(inp, cam, self.rank, self.world, bounds)
+        balanced = self.balanced and bounds is None and self.world > 1
+        color, radii, state = self.backend.forward(inp, cam, self.rank, self.world, bounds, balanced=balanced)
         self.last_num_rendered_local = int(state["R"])
         if assemble:
             color = self.assemble_image(color)

@@ -62,8 +62,12 @@ GCR_API const char* gcr_last_error(void);
  * stripes and this call bins and blends only stripe `shard_rank` (other pixels of out_color are
  * left untouched; radii are global either way; num_rendered counts this stripe's instances).
  * stripe_bounds is a DEVICE array of shard_count + 1 non-decreasing tile-row indices
- * (bounds[0] = 0, bounds[shard_count] = ceil(height / 16)), e.g. from gcr_stripe_partition; NULL
- * means equal-height stripes.  gcr_rasterizer_forward is the NULL form. */
+ * (bounds[0] = 0, bounds[shard_count] = ceil(height / 16)), e.g. from gcr_stripe_partition.  With
+ * stripe_bounds == NULL the stripes are equal-height (balanced == 0; gcr_rasterizer_forward is
+ * this form) or BALANCED (balanced != 0): the projection pass counts the tile instances of every
+ * tile row and cuts the rows into stripes of about equal instance count on the device, at no
+ * extra pass over the inputs.  The cut is deterministic, so ranks that render the same Gaussians
+ * obtain the same bounds without communicating.  The bounds used travel inside geom_buffer. */
 GCR_API int gcr_rasterizer_forward(gcr_alloc_fn geometryBuffer, void* geometry_ctx,
                            gcr_alloc_fn binningBuffer, void* binning_ctx,
                            gcr_alloc_fn imageBuffer, void* image_ctx,
@@ -86,7 +90,7 @@ GCR_API int gcr_rasterizer_forward_striped(gcr_alloc_fn geometryBuffer, void* ge
                            float tan_fovx, float tan_fovy, int prefiltered, float* out_color,
                            int* radii, int debug,
                            int shard_rank, int shard_count, const int* stripe_bounds,
-                           void* cuda_stream);
+                           int balanced, void* cuda_stream);
 
 /* Returns 0, or < 0 on error.  Every element of every gradient array is written (zeros for
  * culled Gaussians): callers need not pre-zero them.  dL_dconic ([P,2,2]), dL_dsh, dL_dscale,
@@ -181,14 +185,15 @@ GCR_API int gcr_peer_barrier(void* const* flag_arrays, int rank, int world, unsi
 enum {
   GCR_GEOM_DEPTH_SORTED_KEYS = 0, /* u32[n_vis] depth keys of the rendered Gaussians, sorted */
   GCR_GEOM_TILES_TOUCHED = 1,     /* u32[P]  tiles inside this rank's stripe */
-  GCR_GEOM_RECORDS = 2,           /* 48 B[P] {x,y,A,B | C,o,r,g | b,idx,2ln(255o),owner} */
+  GCR_GEOM_RECORDS = 2,           /* 48 B[P] {x,y,A,B | C,o,2ln(255o),- | r,g,b,-} */
   GCR_GEOM_CLAMPED = 3,           /* u8[P]   bit ch set if SH colour channel was clamped */
   GCR_GEOM_SORTED_GAUSS = 4,      /* u32[n_vis] Gaussian indices in depth order */
   GCR_GEOM_OFFSETS = 5,           /* u32[n_vis] inclusive scan of tiles_touched in depth order */
   GCR_GEOM_GRAD_ACC = 6,          /* 48 B[P] backward accumulator (single-GPU backward) */
   GCR_GEOM_RADII = 7,             /* i32[P]  internal radii (used when radii == NULL) */
   GCR_GEOM_OWNER = 8,             /* u8[P]   owning rank, 0xFF = culled */
-  GCR_GEOM_COUNTERS = 9,          /* u32[3]  n_vis, num_rendered, overflow flag */
+  GCR_GEOM_COUNTERS = 9,          /* u32[..] [0] n_vis, [1] num_rendered, [2] overflow flag,
+                                     [8..8+shard_count] tile-row stripe bounds of this frame */
   GCR_GEOM_TOTAL_BYTES = 100,
   GCR_BIN_POINT_LIST = 200,       /* u32[R]  sorted instance -> Gaussian index */
   GCR_BIN_TILE_KEYS = 201,        /* u32[R]  sorted tile ids */

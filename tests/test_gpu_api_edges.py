@@ -125,6 +125,38 @@ def test_wrapper_city_frame_gradients_match_reference(built_lib, cuda_device):
     assert rel(leaf.grad, packed) <= 1e-5
 
 
+def test_native_module_matches_ctypes_binding(built_lib, cuda_device):
+    """Seam A as a native module (gaussiancity_b200/compat/diff_gaussian_rasterization_ext, the
+    module the reference's own Python imports) and the ctypes binding are two thin hosts over one
+    C ABI: identical results, bit for bit, on the SH and the colors_precomp path; and the package
+    picked the native one."""
+    from gaussiancity_b200.compat import diff_gaussian_rasterization_ext as native
+    assert g.HOST_BINDING == "native" and g.dgr_ext is native and native.abi_version() == 2
+    for use_sh, deg in [(True, 3), (False, 0)]:
+        s = uniform_scene(30_000, 400, 240, sh_degree=deg, seed=23, device=cuda_device, use_sh=use_sh)
+        G = torch.randn(3, 240, 400, generator=torch.Generator().manual_seed(2)).to(cuda_device)
+        fa = refext.scene_forward_args(s)
+        a = native.rasterize_gaussians(*fa)
+        b = ours.rasterize_gaussians(*fa)
+        assert a[0] == b[0] and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+        ga = native.rasterize_gaussians_backward(*refext.scene_backward_args(s, a[2], G, a[3], a[0], a[4], a[5]))
+        gb = ours.rasterize_gaussians_backward(*refext.scene_backward_args(s, b[2], G, b[3], b[0], b[4], b[5]))
+        for x, y in zip(ga, gb):
+            assert x.shape == y.shape
+            if y.numel():   # L2 reductions are order-nondeterministic at ~1e-7
+                assert (x.double() - y.double()).norm().item() <= 1e-5 * max(y.double().norm().item(), 1e-30)
+        assert torch.equal(native.mark_visible(s.means3D, s.view_matrix, s.proj_matrix),
+                           ours.mark_visible(s.means3D, s.view_matrix, s.proj_matrix))
+    e = torch.Tensor([])
+    with pytest.raises(RuntimeError, match="num_points, 3"):
+        native.rasterize_gaussians(s.bg, torch.zeros(4, 2, device=cuda_device), e, e, e, e, 1.0, e, s.view_matrix,
+                                   s.proj_matrix, 1.0, 1.0, 16, 16, e, 0, s.campos, False, False)
+    with pytest.raises(RuntimeError, match="SH degree"):    # library errors surface as RuntimeError
+        native.rasterize_gaussians(s.bg, s.means3D, e, s.opacities, s.scales, s.rotations, 1.0, e, s.view_matrix,
+                                   s.proj_matrix, s.tanfovx, s.tanfovy, 240, 400,
+                                   torch.zeros(30_000, 4, 3, device=cuda_device), 3, s.campos, False, False)
+
+
 def test_empty_and_fully_culled_inputs(built_lib, cuda_device):
     s = uniform_scene(64, 48, 40, seed=1, device=cuda_device, bg=(0.5, 0.25, 0.125))
     e = torch.Tensor([])

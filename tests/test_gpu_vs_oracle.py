@@ -197,6 +197,7 @@ def test_tile_row_stripes_partition_the_frame(big, balanced):
     dev = color.device
     N, grid_y = 3, (H + 15) // 16
     if balanced:
+        # standalone partition pass; the forward below cuts the same stripes itself (balanced=True)
         ws = torch.empty(grid_y + 1, dtype=torch.int32, device=dev)
         bounds_t = torch.empty(N + 1, dtype=torch.int32, device=dev)
         ours.stripe_partition(s.means3D, s.scales, s.rotations, 1.0, s.view_matrix, s.proj_matrix, s.tanfovx,
@@ -208,14 +209,20 @@ def test_tile_row_stripes_partition_the_frame(big, balanced):
         cnt = [int(ws[bounds[k]:bounds[k + 1]].long().sum()) for k in range(N)]
         assert max(cnt) - min(cnt) <= 2 * int(ws[:grid_y].max())     # balanced to within ~a row
     else:
-        bounds_t, bounds = None, sharding.equal_stripes(grid_y, N)
+        bounds = sharding.equal_stripes(grid_y, N)
     total, Rsum = torch.zeros_like(color), 0
     acc = torch.zeros(P, 12, device=dev, dtype=torch.float64)
     owners = torch.zeros(P, dtype=torch.int32, device=dev)
     states = []
     for k in range(N):
-        (Rk, ck, rk, gk, bk, ik), _ = run_ours(s, shard_rank=k, shard_count=N, stripe_bounds=bounds_t)
+        # rank 0 of the balanced case is also rendered from explicit bounds: same result either way
+        kw = dict(balanced=True) if balanced else {}
+        (Rk, ck, rk, gk, bk, ik), _ = run_ours(s, shard_rank=k, shard_count=N, **kw)
         assert torch.equal(rk, radii)
+        assert ours.stripe_bounds_of(gk, P, N).cpu().tolist() == bounds
+        if balanced and k == 0:
+            (R0, c0, *_), _ = run_ours(s, shard_rank=0, shard_count=N, stripe_bounds=bounds_t)
+            assert R0 == Rk and torch.equal(c0, ck)
         rows = _stripe_rows(bounds, k, H).to(dev)
         assert bool((ck[:, ~rows] == 0).all())
         total += ck

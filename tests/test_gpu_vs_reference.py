@@ -69,8 +69,8 @@ def test_forward_backward_match_reference(ref, built_lib, cuda_device, name, P, 
     assert torch.equal(rec[vis][:, 4:6], gv["conic_opacity"][vis][:, 2:4]), "conic.z/opacity not bit-exact"
     col_src = gv["rgb"] if use_sh else s.colors_precomp
     # SH evaluation is pinned to the reference's contraction order too: colours are bit-exact
-    assert torch.equal(rec[vis][:, 6:9], col_src[vis]), \
-        f"per-Gaussian rgb differs at {(rec[vis][:, 6:9] != col_src[vis]).sum().item()} elements"
+    assert torch.equal(rec[vis][:, 8:11], col_src[vis]), \
+        f"per-Gaussian rgb differs at {(rec[vis][:, 8:11] != col_src[vis]).sum().item()} elements"
     if use_sh:
         cl = ov["clamped"][vis]
         cl3 = torch.stack([(cl & 1) != 0, (cl & 2) != 0, (cl & 4) != 0], dim=1)

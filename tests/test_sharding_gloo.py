@@ -56,9 +56,11 @@ class OracleBackend:
         assert rows.sum() == r.num_rendered
         return torch.tensor(sharding.balanced_stripes(rows.tolist(), world), dtype=torch.int32)
 
-    def forward(self, inp, cam, rank, world, bounds):
+    def forward(self, inp, cam, rank, world, bounds, balanced=False):
         r = self._full(inp, cam)
         gy = (r.H + 15) // 16
+        if bounds is None and balanced:
+            bounds = self.partition(inp, cam, world)
         b = bounds.tolist() if bounds is not None else sharding.equal_stripes(gy, world)
         mask = np.zeros(r.H, dtype=bool)
         mask[b[rank] * 16:min(r.H, b[rank + 1] * 16)] = True

@@ -1,0 +1,180 @@
+#!/usr/bin/env python
+"""BASELINE config 5: the reference's UNMODIFIED models/generator.py G-step (forward, rasterize,
+L1, backward, Adam) on synthetic points + random z, 960x540 render cropped to 640x448, one
+replica per GPU under torchrun DDP -- with the reference rasterizer extension vs ours.
+
+  python tools/config5_gstep.py --arm reference|ours|ours_wrapper [--steps 20] [--points 16384]
+  python -m torch.distributed.run --nproc-per-node 8 ... tools/config5_gstep.py --arm ours
+
+Arms (VERDICT r1 task 6):
+  reference     the reference's own extensions/diff_gaussian_rasterization/__init__.py on top of
+                the unmodified reference CUDA extension (oracle/_ref).
+  ours          THE SAME reference __init__.py, unmodified, on top of our native module
+                `diff_gaussian_rasterization_ext` (gaussiancity_b200/compat, Seam A): the drop-in
+                proof -- nothing of the caller changes.
+  ours_wrapper  gaussiancity_b200.GaussianRasterizerWrapper(fast_camera=True) (Seam B + the
+                host-side camera path of SURVEY 8f-1) handed to the reference's helpers.
+
+The reference's Python is imported from $GCR_REFERENCE_ROOT (default: baseline/_ref/GaussianCity,
+staged by oracle/build_ref.py; /root/reference where it exists).  Dependencies of files on the
+import path that this configuration never executes (spconv / torch_scatter / addict / flash_attn
+for PTv3, plyfile for PLY dumps) are stubbed at import time; README.md:152-161 BLDG settings with
+PTV3.ENABLED = False.  Prints one JSON line (rank 0): it/s per rank, loss curve.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+import types
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def stage_imports(arm):
+    ref_root = os.environ.get("GCR_REFERENCE_ROOT")
+    if not ref_root:
+        ref_root = "/root/reference" if os.path.isdir("/root/reference/models") else \
+            os.path.join(ROOT, "baseline", "_ref", "GaussianCity")
+    if not os.path.isdir(os.path.join(ref_root, "models")):
+        raise SystemExit(f"reference Python not found under {ref_root} (run oracle/build_ref.py)")
+    for name in ("plyfile", "addict", "torch_scatter", "spconv", "spconv.pytorch"):
+        try:
+            __import__(name)
+        except Exception:
+            m = types.ModuleType(name)
+            if name == "addict":
+                m.Dict = dict
+            if name == "spconv":
+                m.pytorch = types.ModuleType("spconv.pytorch")
+                sys.modules["spconv.pytorch"] = m.pytorch
+            if name == "spconv.pytorch":
+                m.SparseModule = object
+            sys.modules[name] = m
+    try:
+        import flash_attn  # noqa: F401
+    except Exception:
+        sys.modules["flash_attn"] = types.ModuleType("flash_attn")
+    sp = sys.modules.get("spconv.pytorch")
+    if sp is not None and not hasattr(sp, "SparseModule"):
+        import torch
+        sp.SparseModule = torch.nn.Module
+    # native modules: the reference's grid_encoder_ext (as is) + one of the two rasterizer modules
+    native = os.path.join(ROOT, "oracle", "_ref") if arm == "reference" else \
+        os.path.join(ROOT, "gaussiancity_b200", "compat")
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))   # grid_encoder_ext
+    sys.path.insert(0, native)                                  # diff_gaussian_rasterization_ext wins from here
+    sys.path.insert(0, ref_root)
+    sys.path.insert(1, ROOT)
+    return ref_root
+
+
+class Cfg(dict):
+    __getattr__ = dict.__getitem__
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--arm", choices=["reference", "ours", "ours_wrapper"], required=True)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--points", type=int, default=16384)
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    dev = torch.device(f"cuda:{int(os.environ.get('LOCAL_RANK', '0'))}")
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ref_root = stage_imports(args.arm)
+    import diff_gaussian_rasterization_ext as native_ext
+    import models.generator
+    import utils.helpers
+    import extensions.diff_gaussian_rasterization as dgr
+    import numpy as np
+
+    # README.md:152-161 (building generator) with PTv3 off; the remaining keys are config.py defaults
+    cfg = Cfg(ENCODER=None, ENCODER_OUT_DIM=3, GLOBAL_ENCODER_N_BLOCKS=6, POS_EMD="SIN_COS",
+              HASH_GRID_N_LEVELS=16, HASH_GRID_LEVEL_DIM=8, SIN_COS_FREQ_BENDS=10, Z_DIM=256,
+              MLP_HIDDEN_DIM=512, MLP_N_SHARED_LAYERS=1, ATTR_FACTORS={"rgb": 2}, ATTR_N_LAYERS={"rgb": 1},
+              PTV3=Cfg(ENABLED=False))
+    n_classes, proj_size, scale_factor = 8, 2048, 0.5
+    torch.manual_seed(1234 + rank)
+    G = models.generator.Generator(cfg, n_classes, proj_size).to(dev)
+    if world > 1:
+        G = torch.nn.parallel.DistributedDataParallel(G, device_ids=[dev.index])
+    opt = torch.optim.Adam(G.parameters(), lr=1e-4, betas=(0.0, 0.999))
+
+    # synthetic batch: lattice points of a ground plane + box buildings seen from a GoogleEarth-style
+    # orbit pose (gaussiancity_b200.synthetic.city_points), [1, N, 9] = xyz | scale | instance | rel_xyz | batch
+    from gaussiancity_b200.synthetic import CITY_K, CITY_SENSOR, city_points
+    pts14, cam_pos, cam_quat = city_points(args.points, seed=7 + rank, device=dev)
+    N = pts14.shape[0]
+    abs_xyz = pts14[None, :, 0:3].contiguous()
+    g = torch.Generator(device="cpu").manual_seed(99 + rank)
+    instances = torch.full((1, N, 1), 10.0, device=dev)
+    classes = torch.randint(0, n_classes, (1, N, 1), generator=g).to(dev)
+    rel_xyz = (torch.rand(1, N, 3, generator=g) * 2 - 1).to(dev)
+    scales = utils.helpers.get_point_scales(torch.ones(1, N, 1, device=dev) * scale_factor, classes, [0, 1])
+    onehots = utils.helpers.get_one_hot(classes, n_classes)
+    bch_idx = torch.zeros(1, N, dtype=torch.long, device=dev)
+    proj_uv = utils.helpers.get_projection_uv(abs_xyz, None, proj_size)
+    rgb = (torch.rand(1, 3, 448, 640, generator=g) * 2 - 1).to(dev)
+    msk = torch.ones(1, 1, 448, 640, device=dev)
+    crp = [dict(x=160, y=46, w=640, h=448)]
+    cam_pos_b, cam_quat_b = [np.asarray(cam_pos, dtype=np.float32)], [np.asarray(cam_quat, dtype=np.float32)]
+
+    if args.arm == "ours_wrapper":
+        import gaussiancity_b200 as ours
+        gr = ours.GaussianRasterizerWrapper(CITY_K, CITY_SENSOR, device=dev, fast_camera=True)
+    else:
+        gr = dgr.GaussianRasterizerWrapper(K=CITY_K, sensor_size=CITY_SENSOR, flip_ud=False, device=dev)
+    l1 = torch.nn.L1Loss()
+    losses = []
+
+    def step(i):
+        torch.manual_seed(5000 + i)      # utils.helpers.get_z draws from the global generator
+        z = utils.helpers.get_z(instances, cfg.Z_DIM)
+        pt_attrs = G(proj_uv, rel_xyz, bch_idx, onehots, z, None, None)
+        gs_pts = utils.helpers.get_gaussian_points(abs_xyz.clone(), scales.clone(), pt_attrs)
+        fake = utils.helpers.get_gaussian_rasterization(gs_pts, gr, cam_pos_b, cam_quat_b, crp)
+        loss = l1(fake * msk, rgb * msk)
+        G.zero_grad()
+        loss.backward()
+        opt.step()
+        return loss
+
+    for i in range(args.warmup):
+        losses.append(float(step(i)))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.warmup, args.warmup + args.steps):
+        losses.append(step(i))
+    e1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    losses = [float(x) for x in losses]
+    ms = e0.elapsed_time(e1) / args.steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    if rank == 0:
+        print(json.dumps({"workload": "config5_generator_gstep", "arm": args.arm, "n_gpus": world,
+                          "points": int(N), "render": "960x540", "crop": "640x448", "steps": args.steps,
+                          "ms_per_step": ms, "it_per_s_per_rank": 1000.0 / ms, "it_per_s_total": world * 1000.0 / ms,
+                          "wall_ms_per_step": wall * 1e3 / args.steps, "losses": losses,
+                          "rasterizer_module": native_ext.__file__.replace(ROOT + "/", ""),
+                          "dgr_python": dgr.__file__.replace(ref_root, "<reference>"),
+                          "generator": "reference models/generator.py, ENCODER=None POS_EMD=SIN_COS Z_DIM=256 PTV3 off"}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
