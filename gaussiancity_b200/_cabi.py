@@ -18,6 +18,8 @@ EXPORTED_SYMBOLS = (
     "gcr_last_error",
     "gcr_rasterizer_forward",
     "gcr_rasterizer_forward_striped",
+    "gcr_rasterizer_forward_window",
+    "gcr_rasterizer_backward_window",
     "gcr_rasterizer_backward",
     "gcr_rasterizer_backward_blend",
     "gcr_rasterizer_backward_geometry",
@@ -66,14 +68,18 @@ def _declare(l):
     l.gcr_rasterizer_forward.argtypes = fwd_args + [c_void_p]
     l.gcr_rasterizer_forward_striped.restype = c_int
     l.gcr_rasterizer_forward_striped.argtypes = fwd_args + [c_void_p, c_int, c_void_p]
+    l.gcr_rasterizer_forward_window.restype = c_int
+    l.gcr_rasterizer_forward_window.argtypes = fwd_args[:-2] + [c_int] * 4 + [c_void_p]
+    bwd_args = ([c_int] * 4 + [c_void_p, c_int, c_int] + [c_void_p] * 4 + [c_float] + [c_void_p] * 5 +
+                [c_float, c_float] + [c_void_p] * 14 + [c_int])
     l.gcr_rasterizer_backward.restype = c_int
-    l.gcr_rasterizer_backward.argtypes = (
-        [c_int] * 4 + [c_void_p, c_int, c_int] + [c_void_p] * 4 + [c_float] + [c_void_p] * 5 +
-        [c_float, c_float] + [c_void_p] * 14 + [c_int, c_int, c_int, c_void_p])
+    l.gcr_rasterizer_backward.argtypes = bwd_args + [c_int, c_int, c_void_p]
+    l.gcr_rasterizer_backward_window.restype = c_int
+    l.gcr_rasterizer_backward_window.argtypes = bwd_args + [c_int] * 4 + [c_void_p]
     l.gcr_rasterizer_backward_blend.restype = c_int
     l.gcr_rasterizer_backward_blend.argtypes = (
         [c_int, c_int, c_void_p, c_int, c_int] + [c_void_p] * 4 + [ctypes.POINTER(c_void_p)] +
-        [c_int] * 6 + [c_void_p])
+        [c_int] * 6 + [ctypes.POINTER(c_int), c_void_p])
     l.gcr_rasterizer_backward_geometry.restype = c_int
     l.gcr_rasterizer_backward_geometry.argtypes = (
         [c_int] * 3 + [c_void_p] * 3 + [c_float] + [c_void_p] * 5 + [c_int, c_int, c_float, c_float] +

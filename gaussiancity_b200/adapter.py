@@ -1,0 +1,89 @@
+"""Adapter fusion: GaussianCity's `utils.helpers.get_gaussian_points` +
+`get_gaussian_rasterization` (utils/helpers.py:226-270) without their intermediate tensors.
+
+The reference builds a `[B, N, 14]` tensor per step -- `cat(xyz, opacity, scales, rotations, rgb)`
+with `ones` for the opacity and identity quaternions for the rotations whenever the generator does
+not predict them (its shipped configurations predict `rgb` only, config.py:128) -- slices it apart
+again in the wrapper (DGR/__init__.py:404-417), renders the full 960x540 frame per batch element
+and then crops 640x448 out of it.  Here the generator's attribute tensors go to the kernels as
+they are (structure of arrays), a missing opacity / rotation is a NULL pointer the projection
+kernel reads as 1 / identity (bit-identical arithmetic, csrc/preprocess.cu), and the crop is a
+pixel window inside the rasterizer: tiles outside it are neither binned nor blended, the output is
+the cropped image, and every pixel of it has exactly the value the full render would give it
+(the tile grid and the camera stay those of the full frame -- DESIGN.md section 8 explains why a
+shifted camera would not be result-preserving).
+"""
+import torch
+
+from . import ext
+
+__all__ = ["render_gaussian_points", "get_gaussian_rasterization_fused"]
+
+
+class _WindowRasterize(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xyz, scales, rgb, opacity, rotations, settings, window):
+        rs = settings
+        R, color, radii, geom, binning, img = ext.rasterize_gaussians_window(
+            rs.bg, xyz, rgb, opacity, scales, rotations, rs.scale_modifier, rs.view_matrix, rs.proj_matrix,
+            rs.tanfovx, rs.tanfovy, rs.img_h, rs.img_w, window, rs.debug)
+        ctx.rs, ctx.window, ctx.R = rs, window, R
+        ctx.has_opacity, ctx.has_rot = opacity is not None, rotations is not None
+        e = torch.Tensor([])
+        ctx.save_for_backward(xyz, scales, rotations if rotations is not None else e, radii, geom, binning, img)
+        return color
+
+    @staticmethod
+    def backward(ctx, grad_color):
+        rs = ctx.rs
+        xyz, scales, rotations, radii, geom, binning, img = ctx.saved_tensors
+        d_xyz, d_rgb, d_scales, d_opacity, d_rot, _ = ext.rasterize_gaussians_backward_window(
+            rs.bg, xyz, radii, scales, rotations if ctx.has_rot else None, rs.scale_modifier, rs.view_matrix,
+            rs.proj_matrix, rs.tanfovx, rs.tanfovy, rs.img_h, rs.img_w, ctx.window, grad_color, geom, ctx.R,
+            binning, img, want_opacity=ctx.has_opacity, debug=rs.debug)
+        return d_xyz, d_scales, d_rgb, d_opacity, d_rot, None, None
+
+
+def render_gaussian_points(xyz, scales, rgb, wrapper, cam_position, cam_quaternion, opacity=None,
+                           rotations=None, crop=None):
+    """One frame: xyz/scales/rgb [N,3] (+ optional opacity [N,1], rotations [N,4]) through
+    `wrapper` (a gaussiancity_b200.GaussianRasterizerWrapper: camera, flips) -> image [3,h,w].
+    crop = dict(x=, y=, w=, h=) in the coordinates of the wrapper's OUTPUT image (after its flips),
+    exactly like the slice in utils/helpers.py:261-267; None = the full frame."""
+    rs = wrapper._get_gaussian_rasterization_settings(cam_position, cam_quaternion)
+    W, H = int(rs.img_w), int(rs.img_h)
+    if crop is None:
+        x, y, w, h = 0, 0, W, H
+    else:
+        x, y, w, h = int(crop["x"]), int(crop["y"]), int(crop["w"]), int(crop["h"])
+    # the wrapper flips the rendered image (DGR/__init__.py:421-424): map the crop back through the flips
+    if wrapper.flip_lr:
+        x = W - (x + w)
+    if wrapper.flip_ud:
+        y = H - (y + h)
+    img = _WindowRasterize.apply(xyz, scales, rgb, opacity, rotations, rs, (x, y, w, h))
+    if wrapper.flip_lr:
+        img = torch.flip(img, dims=[2])
+    if wrapper.flip_ud:
+        img = torch.flip(img, dims=[1])
+    return img
+
+
+def get_gaussian_rasterization_fused(xyz, scales, attrs, wrapper, cam_pos, cam_quat, crop_bboxes=None):
+    """Drop-in for get_gaussian_points + get_gaussian_rasterization (utils/helpers.py:226-270):
+    xyz [B,N,3], scales [B,N,3], attrs = the generator's output dict (rgb; optionally xyz offsets,
+    scale factors, opacity) -> images [B,3,h,w].  Unlike the reference this does not modify xyz /
+    scales in place."""
+    rgb = attrs["rgb"]
+    if "xyz" in attrs:
+        xyz = xyz + attrs["xyz"]
+    if "scale" in attrs:
+        scales = scales * attrs["scale"]
+    opacity = attrs.get("opacity")
+    images = []
+    for i in range(xyz.size(0)):
+        images.append(render_gaussian_points(
+            xyz[i], scales[i], rgb[i], wrapper, cam_pos[i], cam_quat[i],
+            opacity=None if opacity is None else opacity[i],
+            crop=None if crop_bboxes is None else crop_bboxes[i]))
+    return torch.stack(images, dim=0)

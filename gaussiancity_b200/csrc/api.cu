@@ -211,7 +211,7 @@ int forward_impl(gcr_alloc_fn geometryBuffer, void* geometry_ctx, gcr_alloc_fn b
                  const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
                  const float* cam_pos, float tan_fovx, float tan_fovy, int prefiltered,
                  float* out_color, int* radii, int debug, int shard_rank, int shard_count,
-                 const int* stripe_bounds, int balanced, void* cuda_stream) {
+                 const int* stripe_bounds, int balanced, const int* window, void* cuda_stream) {
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
   if (P <= 0) return 0;
   prof_next_call();
@@ -219,7 +219,7 @@ int forward_impl(gcr_alloc_fn geometryBuffer, void* geometry_ctx, gcr_alloc_fn b
   if (!valid_shard(shard_rank, shard_count)) return fail("invalid tile-row shard (rank, count)");
   if (colors_precomp == nullptr && shs == nullptr)
     return fail("provide either SHs or precomputed colours");
-  if (cov3D_precomp == nullptr && (scales == nullptr || rotations == nullptr))
+  if (cov3D_precomp == nullptr && scales == nullptr)   // rotations == NULL alone: identity rotation
     return fail("provide either scale/rotation or a precomputed 3D covariance");
   if (D < 0 || D > 3 || (colors_precomp == nullptr && (D + 1) * (D + 1) > M))
     return fail("SH degree does not fit the coefficient count");
@@ -227,9 +227,9 @@ int forward_impl(gcr_alloc_fn geometryBuffer, void* geometry_ctx, gcr_alloc_fn b
     return fail("at most 16 SH coefficients per Gaussian (degree 3) are supported");
   if (geometryBuffer == nullptr || binningBuffer == nullptr || imageBuffer == nullptr)
     return fail("buffer callbacks must not be NULL");
-  if (means3D == nullptr || opacities == nullptr || viewmatrix == nullptr || projmatrix == nullptr ||
-      background == nullptr || out_color == nullptr)
-    return fail("means3D, opacities, viewmatrix, projmatrix, background and out_color must not be NULL");
+  if (means3D == nullptr || viewmatrix == nullptr || projmatrix == nullptr || background == nullptr ||
+      out_color == nullptr)   // opacities == NULL: every Gaussian opaque (opacity 1)
+    return fail("means3D, viewmatrix, projmatrix, background and out_color must not be NULL");
   if (colors_precomp == nullptr && cam_pos == nullptr) return fail("cam_pos must not be NULL with SHs");
   // vector loads: rotations are read as float4, SH rows as 32-byte (M = 16) or 16-byte words
   if (rotations != nullptr && (reinterpret_cast<uintptr_t>(rotations) & 15u) != 0)
@@ -243,6 +243,16 @@ int forward_impl(gcr_alloc_fn geometryBuffer, void* geometry_ctx, gcr_alloc_fn b
   const int tiles = grid_x * grid_y;
   const size_t npix = (size_t)width * height;
   if (grid_x > 4095 || grid_y > 4095) return fail("images above 65520 pixels a side are not supported");
+  // pixel window (a crop folded into the rasterizer): tiles outside it are neither binned nor blended
+  int win[4] = {0, 0, width, height};
+  if (window != nullptr) {
+    if (shard_count != 1) return fail("a pixel window cannot be combined with tile-row stripes");
+    for (int k = 0; k < 4; ++k) win[k] = window[k];
+    if (win[0] < 0 || win[1] < 0 || win[2] <= 0 || win[3] <= 0 || win[0] + win[2] > width || win[1] + win[3] > height)
+      return fail("pixel window must lie inside the image");
+  }
+  const int wc0 = win[0] / GCR_TILE_X, wc1 = (win[0] + win[2] + GCR_TILE_X - 1) / GCR_TILE_X;
+  const int wr0 = win[1] / GCR_TILE_Y, wr1 = (win[1] + win[3] + GCR_TILE_Y - 1) / GCR_TILE_Y;
   int dev = 0;
   GCR_CUDA_OK(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) return fail("device ordinal out of range");
@@ -302,6 +312,7 @@ int forward_impl(gcr_alloc_fn geometryBuffer, void* geometry_ctx, gcr_alloc_fn b
   pa.focal_x = width / (2.0f * tan_fovx);
   pa.grid_x = grid_x; pa.grid_y = grid_y;
   pa.shard_rank = shard_rank; pa.shard_count = shard_count; pa.stripe_bounds = bounds_dev;
+  pa.win_col0 = wc0; pa.win_col1 = wc1; pa.win_row0 = wr0; pa.win_row1 = wr1;
   pa.prefiltered = prefiltered != 0;
   pa.radii = radii; pa.tiles_touched = tiles_touched; pa.depth_keys = keys_a;
   pa.records = records; pa.rects = reinterpret_cast<uint2*>(gptr + gl.rects);
@@ -397,6 +408,8 @@ int forward_impl(gcr_alloc_fn geometryBuffer, void* geometry_ctx, gcr_alloc_fn b
   GcrBlendArgs ba;
   memset(&ba, 0, sizeof(ba));
   ba.W = width; ba.H = height; ba.grid_x = grid_x; ba.grid_y = grid_y;
+  ba.tile_x0 = wc0; ba.tile_y0 = wr0; ba.tiles_x = wc1 - wc0; ba.tiles_y = wr1 - wr0;
+  ba.px0 = win[0]; ba.py0 = win[1]; ba.pw = win[2]; ba.ph = win[3];
   ba.stripe = stripe;
   ba.ranges = ranges; ba.point_list = tv_a; ba.records = records; ba.bg = background;
   ba.final_T = reinterpret_cast<float*>(iptr + il.final_T);
@@ -430,7 +443,7 @@ int gcr_rasterizer_forward(gcr_alloc_fn geometryBuffer, void* geometry_ctx,
                       P, D, M, background, width, height, means3D, shs, colors_precomp, opacities,
                       scales, scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix, cam_pos,
                       tan_fovx, tan_fovy, prefiltered, out_color, radii, debug, shard_rank, shard_count,
-                      nullptr, 0, cuda_stream);
+                      nullptr, 0, nullptr, cuda_stream);
 }
 
 int gcr_rasterizer_forward_striped(gcr_alloc_fn geometryBuffer, void* geometry_ctx,
@@ -450,17 +463,45 @@ int gcr_rasterizer_forward_striped(gcr_alloc_fn geometryBuffer, void* geometry_c
                       P, D, M, background, width, height, means3D, shs, colors_precomp, opacities,
                       scales, scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix, cam_pos,
                       tan_fovx, tan_fovy, prefiltered, out_color, radii, debug, shard_rank, shard_count,
-                      stripe_bounds, balanced, cuda_stream);
+                      stripe_bounds, balanced, nullptr, cuda_stream);
+}
+
+int gcr_rasterizer_forward_window(gcr_alloc_fn geometryBuffer, void* geometry_ctx,
+                                  gcr_alloc_fn binningBuffer, void* binning_ctx,
+                                  gcr_alloc_fn imageBuffer, void* image_ctx, int P, int D, int M,
+                                  const float* background, int width, int height,
+                                  const float* means3D, const float* shs,
+                                  const float* colors_precomp, const float* opacities,
+                                  const float* scales, float scale_modifier,
+                                  const float* rotations, const float* cov3D_precomp,
+                                  const float* viewmatrix, const float* projmatrix,
+                                  const float* cam_pos, float tan_fovx, float tan_fovy,
+                                  int prefiltered, float* out_color, int* radii, int debug,
+                                  int win_x, int win_y, int win_w, int win_h, void* cuda_stream) {
+  const int window[4] = {win_x, win_y, win_w, win_h};
+  return forward_impl(geometryBuffer, geometry_ctx, binningBuffer, binning_ctx, imageBuffer, image_ctx,
+                      P, D, M, background, width, height, means3D, shs, colors_precomp, opacities,
+                      scales, scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix, cam_pos,
+                      tan_fovx, tan_fovy, prefiltered, out_color, radii, debug, 0, 1, nullptr, 0, window,
+                      cuda_stream);
 }
 
 int gcr_rasterizer_backward_blend(int P, int R, const float* background, int width, int height,
                                   char* geom_buffer, char* binning_buffer, char* image_buffer,
                                   const float* dL_dpix, float* const* accumulators,
                                   int n_accumulators, int zero_first, int remote_scalar_atomics,
-                                  int debug, int shard_rank, int shard_count, void* cuda_stream) {
+                                  int debug, int shard_rank, int shard_count, const int* window,
+                                  void* cuda_stream) {
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
   if (P <= 0) return 0;
   if (!valid_shard(shard_rank, shard_count)) return fail("invalid tile-row shard (rank, count)");
+  int win[4] = {0, 0, width, height};
+  if (window != nullptr) {
+    if (shard_count != 1) return fail("a pixel window cannot be combined with tile-row stripes");
+    for (int k = 0; k < 4; ++k) win[k] = window[k];
+    if (win[0] < 0 || win[1] < 0 || win[2] <= 0 || win[3] <= 0 || win[0] + win[2] > width || win[1] + win[3] > height)
+      return fail("pixel window must lie inside the image");
+  }
   if (width <= 0 || height <= 0) return fail("image size must be positive");
   if (accumulators == nullptr || (n_accumulators != 1 && n_accumulators != shard_count))
     return fail("accumulators: pass 1 pointer, or one per rank of the striped frame");
@@ -492,6 +533,10 @@ int gcr_rasterizer_backward_blend(int P, int R, const float* background, int wid
   GcrBlendArgs ba;
   memset(&ba, 0, sizeof(ba));
   ba.W = width; ba.H = height; ba.grid_x = grid_x; ba.grid_y = grid_y;
+  ba.tile_x0 = win[0] / GCR_TILE_X; ba.tile_y0 = win[1] / GCR_TILE_Y;
+  ba.tiles_x = (win[0] + win[2] + GCR_TILE_X - 1) / GCR_TILE_X - ba.tile_x0;
+  ba.tiles_y = (win[1] + win[3] + GCR_TILE_Y - 1) / GCR_TILE_Y - ba.tile_y0;
+  ba.px0 = win[0]; ba.py0 = win[1]; ba.pw = win[2]; ba.ph = win[3];
   ba.stripe = shard_count > 1
                   ? reinterpret_cast<const int*>(counters + GCR_CNT_STRIPE_BOUNDS) + shard_rank : nullptr;
   ba.ranges = reinterpret_cast<const uint2*>(iptr + il.ranges);
@@ -531,14 +576,13 @@ int gcr_rasterizer_backward_geometry(int P, int D, int M, const float* means3D, 
   if (range_start < 0 || range_start + range_count > P) return fail("Gaussian range out of bounds");
   if (shard_rank < 0 || shard_rank >= GCR_MAX_SHARDS) return fail("invalid tile-row shard (rank, count)");
   if (width <= 0 || height <= 0) return fail("image size must be positive");
-  if (cov3D_precomp == nullptr && (scales == nullptr || rotations == nullptr))
+  if (cov3D_precomp == nullptr && scales == nullptr)   // rotations == NULL alone: identity rotation
     return fail("provide either scale/rotation or a precomputed 3D covariance");
   if (means3D == nullptr || viewmatrix == nullptr || projmatrix == nullptr || geom_buffer == nullptr ||
       accumulator == nullptr)
     return fail("means3D, viewmatrix, projmatrix, geom_buffer and accumulator must not be NULL");
-  if (dL_dmean2D == nullptr || dL_dopacity == nullptr || dL_dcolor == nullptr || dL_dmean3D == nullptr ||
-      dL_dcov3D == nullptr)
-    return fail("dL_dmean2D, dL_dopacity, dL_dcolor, dL_dmean3D and dL_dcov3D must not be NULL");
+  if (dL_dmean2D == nullptr || dL_dcolor == nullptr || dL_dmean3D == nullptr || dL_dcov3D == nullptr)
+    return fail("dL_dmean2D, dL_dcolor, dL_dmean3D and dL_dcov3D must not be NULL");
   if ((reinterpret_cast<uintptr_t>(accumulator) & 15u) != 0) return fail("accumulators must be 16-byte aligned");
   if (shs != nullptr && M > 16) return fail("at most 16 SH coefficients per Gaussian (degree 3) are supported");
   if (shs != nullptr && M > 0 && dL_dsh == nullptr) return fail("dL_dsh must not be NULL with SHs");
@@ -572,10 +616,11 @@ int gcr_rasterizer_backward_geometry(int P, int D, int M, const float* means3D, 
   a.focal_x = width / (2.0f * tan_fovx);
   a.tan_fovx = tan_fovx; a.tan_fovy = tan_fovy;
   a.grad_acc = reinterpret_cast<GcrGradAcc*>(accumulator);
+  a.ticket = reinterpret_cast<uint32_t*>(gptr + gl.counters) + GCR_CNT_BWD_TICKET;
   a.dL_dmean2D = dL_dmean2D; a.dL_dconic = dL_dconic; a.dL_dopacity = dL_dopacity;
   a.dL_dcolor = dL_dcolor; a.dL_dmean3D = dL_dmean3D; a.dL_dcov3D = dL_dcov3D;
   a.dL_dsh = dL_dsh; a.dL_dscale = (scales != nullptr) ? dL_dscale : nullptr;
-  a.dL_drot = (scales != nullptr) ? dL_drot : nullptr;
+  a.dL_drot = (scales != nullptr && rotations != nullptr) ? dL_drot : nullptr;
   prof_mark(ST_GEOM_BWD, 0, stream);
   GCR_LAUNCH("preprocess_bwd", gcr_launch_preprocess_bwd(a, stream), debug, stream);
   prof_mark(ST_GEOM_BWD, 1, stream);
@@ -589,6 +634,52 @@ int gcr_rasterizer_backward_geometry(int P, int D, int M, const float* means3D, 
                                   sizeof(float) * 4 * (size_t)range_count, stream));
   }
   return 0;
+}
+
+namespace {
+int backward_impl(int P, int D, int M, int R, const float* background, int width, int height,
+                  const float* means3D, const float* shs, const float* scales, float scale_modifier,
+                  const float* rotations, const float* cov3D_precomp, const float* viewmatrix,
+                  const float* projmatrix, const float* campos, float tan_fovx, float tan_fovy,
+                  const int* radii, char* geom_buffer, char* binning_buffer, char* image_buffer,
+                  const float* dL_dpix, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
+                  float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale,
+                  float* dL_drot, int debug, const int* window, void* cuda_stream) {
+  if (P <= 0) return 0;
+  if (geom_buffer == nullptr) return fail("geom_buffer must not be NULL");
+  const GeomLayout gl((size_t)P);
+  float* grad_acc = reinterpret_cast<float*>(align256(geom_buffer) + gl.grad_acc);
+  int rc = gcr_rasterizer_backward_blend(P, R, background, width, height, geom_buffer, binning_buffer,
+                                         image_buffer, dL_dpix, &grad_acc, 1, 1, 0, debug, 0, 1, window,
+                                         cuda_stream);
+  if (rc < 0) return rc;
+  return gcr_rasterizer_backward_geometry(P, D, M, means3D, shs, scales, scale_modifier, rotations,
+                                          cov3D_precomp, viewmatrix, projmatrix, campos, width,
+                                          height, tan_fovx, tan_fovy, radii, geom_buffer, grad_acc,
+                                          dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor,
+                                          dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, debug,
+                                          0, -1, 0, 0, 0, cuda_stream);
+}
+}  // namespace
+
+int gcr_rasterizer_backward_window(int P, int D, int M, int R, const float* background, int width,
+                                   int height, const float* means3D, const float* shs,
+                                   const float* colors_precomp, const float* scales,
+                                   float scale_modifier, const float* rotations,
+                                   const float* cov3D_precomp, const float* viewmatrix,
+                                   const float* projmatrix, const float* campos, float tan_fovx,
+                                   float tan_fovy, const int* radii, char* geom_buffer,
+                                   char* binning_buffer, char* image_buffer, const float* dL_dpix,
+                                   float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
+                                   float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D,
+                                   float* dL_dsh, float* dL_dscale, float* dL_drot, int debug,
+                                   int win_x, int win_y, int win_w, int win_h, void* cuda_stream) {
+  (void)colors_precomp;
+  const int window[4] = {win_x, win_y, win_w, win_h};
+  return backward_impl(P, D, M, R, background, width, height, means3D, shs, scales, scale_modifier, rotations,
+                       cov3D_precomp, viewmatrix, projmatrix, campos, tan_fovx, tan_fovy, radii, geom_buffer,
+                       binning_buffer, image_buffer, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor,
+                       dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, debug, window, cuda_stream);
 }
 
 int gcr_rasterizer_backward(int P, int D, int M, int R, const float* background, int width,
@@ -608,19 +699,10 @@ int gcr_rasterizer_backward(int P, int D, int M, int R, const float* background,
   if (shard_count != 1 || shard_rank != 0)
     return fail("gcr_rasterizer_backward handles single-stripe frames; a striped frame goes through "
                 "gcr_rasterizer_backward_blend / _geometry");
-  if (geom_buffer == nullptr) return fail("geom_buffer must not be NULL");
-  const GeomLayout gl((size_t)P);
-  float* grad_acc = reinterpret_cast<float*>(align256(geom_buffer) + gl.grad_acc);
-  int rc = gcr_rasterizer_backward_blend(P, R, background, width, height, geom_buffer, binning_buffer,
-                                         image_buffer, dL_dpix, &grad_acc, 1, 1, 0, debug, 0, 1,
-                                         cuda_stream);
-  if (rc < 0) return rc;
-  return gcr_rasterizer_backward_geometry(P, D, M, means3D, shs, scales, scale_modifier, rotations,
-                                          cov3D_precomp, viewmatrix, projmatrix, campos, width,
-                                          height, tan_fovx, tan_fovy, radii, geom_buffer, grad_acc,
-                                          dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor,
-                                          dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, debug,
-                                          0, -1, 0, 0, 0, cuda_stream);
+  return backward_impl(P, D, M, R, background, width, height, means3D, shs, scales, scale_modifier, rotations,
+                       cov3D_precomp, viewmatrix, projmatrix, campos, tan_fovx, tan_fovy, radii, geom_buffer,
+                       binning_buffer, image_buffer, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor,
+                       dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, debug, nullptr, cuda_stream);
 }
 
 int gcr_rasterizer_mark_visible(int P, const float* means3D, const float* viewmatrix,

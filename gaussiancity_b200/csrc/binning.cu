@@ -222,14 +222,18 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
     const bool valid = i < n && !(kFirstDepth && key[r] == kInvalidKey);
     const unsigned vmask = __ballot_sync(0xffffffffu, valid);
     pos16[r] = 0xFFFFu;
+    uint32_t d = 0, before = 0;
+    unsigned m = 0;
     if (valid) {
-      const uint32_t d = (key[r] >> shift) & digit_mask;
-      const unsigned m = digit_peers(d, nbits, vmask);
-      const uint32_t before = warp_hist[warp][d];
+      d = (key[r] >> shift) & digit_mask;
+      m = digit_peers(d, nbits, vmask);
+      before = warp_hist[warp][d];
+    }
+    __syncwarp();   // every lane: the counters read above are rewritten below, and read again next round
+    if (valid && (m & ((1u << lane) - 1)) == 0) warp_hist[warp][d] = before + __popc(m);
+    __syncwarp();
+    if (valid) {
       const uint32_t pos = before + __popc(m & ((1u << lane) - 1));
-      __syncwarp(vmask);
-      if ((m & ((1u << lane) - 1)) == 0) warp_hist[warp][d] = before + __popc(m);
-      __syncwarp(vmask);
       st_keys[pos] = key[r];
       pos16[r] = (uint16_t)pos;
     }
@@ -281,10 +285,8 @@ cudaError_t launch_onesweep_pass(unsigned tiles, cudaStream_t stream, const uint
                                  const uint32_t* ghist, uint32_t* st, uint32_t* ticket,
                                  uint32_t* n_out) {
   constexpr int smem = ((kThreads / 32) * kBins + 2 * kBins + 16 + 2 * kThreads * kItems) * 4;
-  // the opt-in shared-memory size is a per-device attribute; setting it is idempotent and cheap
-  // (no static "configured" table: this function may be called from any thread on any device)
-  cudaError_t e = cudaFuncSetAttribute(onesweep_pass_kernel<kFirstDepth, kThreads, kItems>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  static std::atomic<unsigned long long> configured{0ull};   // one per template instance
+  cudaError_t e = gcr_set_dynamic_smem_once(onesweep_pass_kernel<kFirstDepth, kThreads, kItems>, smem, configured);
   if (e != cudaSuccess) return e;
   onesweep_pass_kernel<kFirstDepth, kThreads, kItems><<<tiles, kThreads, smem, stream>>>(
       kin, vin, kout, vout, n_max, n_ptr, shift, mask, bits, ghist, st, ticket, n_out);

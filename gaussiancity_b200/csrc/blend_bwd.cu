@@ -65,10 +65,10 @@ blend_bwd_kernel(GcrBlendArgs a) {
   int* slot_j = reinterpret_cast<int*>(panel + kWarpPanelFloats);
   float4* pxc = reinterpret_cast<float4*>(slot_j + kSlots);
 
-  const int tile_x = blockIdx.x;
-  int tile_y = (int)blockIdx.y;
+  const int tile_x = a.tile_x0 + (int)blockIdx.x;
+  int tile_y = a.tile_y0 + (int)blockIdx.y;
   if (a.stripe != nullptr) {
-    tile_y += a.stripe[0];
+    tile_y = a.stripe[0] + (int)blockIdx.y;
     if (tile_y >= a.stripe[1]) return;   // grid covers every row; the stripe is device-side
   }
   const uint2 range = a.ranges[tile_y * a.grid_x + tile_x];
@@ -78,20 +78,22 @@ blend_bwd_kernel(GcrBlendArgs a) {
   const int sub_y0 = tile_y * GCR_TILE_Y + (warp >> 1) * 4;
   const int pix_x = sub_x0 + (lane & 7);
   const int pix_y = sub_y0 + (lane >> 3);
-  const bool inside = pix_x < a.W && pix_y < a.H;
+  const bool inside = pix_x < a.W && pix_y < a.H && pix_x >= a.px0 && pix_x < a.px0 + a.pw && pix_y >= a.py0 &&
+                      pix_y < a.py0 + a.ph;
   const float pxf = (float)pix_x, pyf = (float)pix_y;
   const float rx0 = (float)sub_x0, rx1 = (float)(sub_x0 + 7);
   const float ry0 = (float)sub_y0, ry1 = (float)(sub_y0 + 3);
   const int pix_id = a.W * pix_y + pix_x;
-  const size_t plane = (size_t)a.H * a.W;
+  const size_t win_id = (size_t)a.pw * (pix_y - a.py0) + (pix_x - a.px0);   // index into dL_dpix
+  const size_t plane = (size_t)a.ph * a.pw;
 
   const float T_final = inside ? a.final_T[pix_id] : 0.f;
   const int last_contributor = inside ? (int)a.n_contrib[pix_id] : 0;
   float dLp0 = 0.f, dLp1 = 0.f, dLp2 = 0.f;
   if (inside) {
-    dLp0 = a.dL_dpix[pix_id];
-    dLp1 = a.dL_dpix[plane + pix_id];
-    dLp2 = a.dL_dpix[2 * plane + pix_id];
+    dLp0 = a.dL_dpix[win_id];
+    dLp1 = a.dL_dpix[plane + win_id];
+    dLp2 = a.dL_dpix[2 * plane + win_id];
   }
   pxc[(lane >> 3) * 9 + (lane & 7)] = make_float4(dLp0, dLp1, dLp2, 0.f);  // row stride 9: no bank conflicts
   const float bg_dot_dpixel = a.bg[0] * dLp0 + a.bg[1] * dLp1 + a.bg[2] * dLp2;
@@ -301,11 +303,10 @@ blend_bwd_kernel(GcrBlendArgs a) {
 }  // namespace
 
 cudaError_t gcr_launch_blend_bwd(const GcrBlendArgs& a, cudaStream_t stream) {
-  if (a.grid_y <= 0 || a.grid_x <= 0) return cudaSuccess;
-  dim3 grid(a.grid_x, a.grid_y, 1);
-  // per-device attribute; idempotent and cheap, so no unsynchronised "configured" table
-  cudaError_t e = cudaFuncSetAttribute(blend_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       kBwdSmemBytes);
+  if (a.tiles_x <= 0 || a.tiles_y <= 0) return cudaSuccess;
+  dim3 grid(a.tiles_x, a.stripe != nullptr ? a.grid_y : a.tiles_y, 1);
+  static std::atomic<unsigned long long> configured{0ull};
+  cudaError_t e = gcr_set_dynamic_smem_once(blend_bwd_kernel, kBwdSmemBytes, configured);
   if (e != cudaSuccess) return e;
   blend_bwd_kernel<<<grid, kBlendThreads, kBwdSmemBytes, stream>>>(a);
   return cudaGetLastError();

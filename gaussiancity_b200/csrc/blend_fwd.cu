@@ -31,10 +31,10 @@ blend_fwd_kernel(GcrBlendArgs a) {
   __shared__ __align__(8) uint64_t full_bar[kBlendStages];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tile_x = blockIdx.x;
-  int tile_y = (int)blockIdx.y;
+  const int tile_x = a.tile_x0 + (int)blockIdx.x;
+  int tile_y = a.tile_y0 + (int)blockIdx.y;
   if (a.stripe != nullptr) {
-    tile_y += a.stripe[0];
+    tile_y = a.stripe[0] + (int)blockIdx.y;
     if (tile_y >= a.stripe[1]) return;   // grid covers every row; the stripe is device-side
   }
   const uint2 range = a.ranges[tile_y * a.grid_x + tile_x];
@@ -45,7 +45,9 @@ blend_fwd_kernel(GcrBlendArgs a) {
   const int sub_y0 = tile_y * GCR_TILE_Y + (warp >> 1) * 4;
   const int pix_x = sub_x0 + (lane & 7);
   const int pix_y = sub_y0 + (lane >> 3);
-  const bool inside = pix_x < a.W && pix_y < a.H;
+  // pixels of the frame that are also inside the pixel window (the whole frame by default)
+  const bool inside = pix_x < a.W && pix_y < a.H && pix_x >= a.px0 && pix_x < a.px0 + a.pw && pix_y >= a.py0 &&
+                      pix_y < a.py0 + a.ph;
   const float pxf = (float)pix_x, pyf = (float)pix_y;
   const float rx0 = (float)sub_x0, rx1 = (float)(sub_x0 + 7);
   const float ry0 = (float)sub_y0, ry1 = (float)(sub_y0 + 3);
@@ -134,20 +136,21 @@ blend_fwd_kernel(GcrBlendArgs a) {
 
   if (inside) {
     const int pix_id = a.W * pix_y + pix_x;
-    const size_t plane = (size_t)a.H * a.W;
     a.final_T[pix_id] = T;
     a.n_contrib[pix_id] = last_contributor;
-    a.out_color[pix_id] = __fmaf_rn(T, a.bg[0], C0);
-    a.out_color[plane + pix_id] = __fmaf_rn(T, a.bg[1], C1);
-    a.out_color[2 * plane + pix_id] = __fmaf_rn(T, a.bg[2], C2);
+    const size_t out_id = (size_t)a.pw * (pix_y - a.py0) + (pix_x - a.px0);
+    const size_t plane = (size_t)a.ph * a.pw;
+    a.out_color[out_id] = __fmaf_rn(T, a.bg[0], C0);
+    a.out_color[plane + out_id] = __fmaf_rn(T, a.bg[1], C1);
+    a.out_color[2 * plane + out_id] = __fmaf_rn(T, a.bg[2], C2);
   }
 }
 
 }  // namespace
 
 cudaError_t gcr_launch_blend_fwd(const GcrBlendArgs& a, cudaStream_t stream) {
-  if (a.grid_y <= 0 || a.grid_x <= 0) return cudaSuccess;
-  dim3 grid(a.grid_x, a.grid_y, 1);
+  if (a.tiles_x <= 0 || a.tiles_y <= 0) return cudaSuccess;
+  dim3 grid(a.tiles_x, a.stripe != nullptr ? a.grid_y : a.tiles_y, 1);
   blend_fwd_kernel<<<grid, kBlendThreads, 0, stream>>>(a);
   return cudaGetLastError();
 }

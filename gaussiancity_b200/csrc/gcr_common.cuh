@@ -166,3 +166,21 @@ __forceinline__ __device__ void gcr_stg_v8(float* p, const float (&v)[8]) {
 }
 
 static inline size_t gcr_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Opt-in dynamic shared-memory size: a per-device function attribute that costs microseconds to
+// set, so it is set once per (kernel, device).  `mask` is one std::atomic<uint64_t> per kernel
+// (bit = device ordinal): safe from any host thread, no lock, and the return code is propagated.
+#ifdef __cplusplus
+#include <atomic>
+template <typename Kernel>
+static inline cudaError_t gcr_set_dynamic_smem_once(Kernel kernel, int bytes, std::atomic<unsigned long long>& mask) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const unsigned long long bit = (dev >= 0 && dev < 64) ? (1ull << dev) : 0ull;
+  if (bit != 0ull && (mask.load(std::memory_order_acquire) & bit) != 0ull) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && bit != 0ull) mask.fetch_or(bit, std::memory_order_release);
+  return e;
+}
+#endif

@@ -9,7 +9,8 @@ struct GcrGradAcc;
 
 // Device-side counters of one forward call (uint32 words at the start of a 256-byte block in
 // the geometry buffer): nothing downstream of the preprocess needs a count on the host.
-enum { GCR_CNT_NVIS = 0, GCR_CNT_R = 1, GCR_CNT_OVERFLOW = 2, GCR_CNT_TOTAL_TILES64 = 4 /* 2 words */,
+enum { GCR_CNT_NVIS = 0, GCR_CNT_R = 1, GCR_CNT_OVERFLOW = 2, GCR_CNT_BWD_TICKET = 3,
+       GCR_CNT_TOTAL_TILES64 = 4 /* 2 words */,
        GCR_CNT_STRIPE_BOUNDS = 8 /* int[GCR_MAX_RANKS + 1] */, GCR_CNT_WORDS = 64 };
 
 constexpr int GCR_MAX_RANKS = 16;          // tile-row stripes / peers of one frame
@@ -35,6 +36,9 @@ struct GcrPreprocessArgs {
   // must be 1) means one stripe covering every row.  DEVICE pointer: no host round trip.
   int shard_rank, shard_count;
   const int* stripe_bounds;
+  // tile window [win_col0, win_col1) x [win_row0, win_row1): only tiles inside it are binned (a
+  // crop folded into the rasterizer; the full grid by default)
+  int win_col0, win_col1, win_row0, win_row1;
   bool prefiltered;
   // outputs
   int* radii;               // global screen-space radius (0 = culled everywhere)
@@ -112,7 +116,12 @@ cudaError_t gcr_launch_tile_ranges(uint32_t n_max, const uint32_t* n_ptr, const 
 // ---- blend (blend_fwd.cu / blend_bwd.cu) -----------------------------------------------------
 struct GcrBlendArgs {
   int W, H, grid_x, grid_y;
-  const int* stripe;           // device {row0,row1} or null = all rows
+  // one CTA per tile of the host-known tile window (origin tile_x0, tile_y0; tiles_x x tiles_y),
+  // or, with `stripe`, per tile of rows [stripe[0], stripe[1]) (grid covers every row)
+  int tile_x0, tile_y0, tiles_x, tiles_y;
+  // pixel window: out_color / dL_dpix are [3, ph, pw] images holding pixels [px0, px0+pw) x [py0, py0+ph)
+  int px0, py0, pw, ph;
+  const int* stripe;           // device {row0,row1} or null
   const uint2* ranges;
   const uint32_t* point_list;  // sorted instance -> Gaussian index
   const GcrRecord* records;    // per-Gaussian records, gathered through point_list
@@ -154,6 +163,7 @@ struct GcrPreprocessBwdArgs {
   const float* campos;
   float focal_x, focal_y, tan_fovx, tan_fovy;
   GcrGradAcc* grad_acc;
+  uint32_t* ticket;              // chunk dispenser (one word; the launcher zeroes it)
   // outputs (every element written exactly once; no pre-zeroing required)
   float* dL_dmean2D;   // [P,3]
   float* dL_dconic;    // [P,4] or null

@@ -67,7 +67,10 @@ __forceinline__ __device__ bool gcr_project(const GcrPreprocessArgs& a, int idx,
     const float s0 = __fmul_rn(a.scale_modifier, a.scales[3 * idx + 0]);
     const float s1 = __fmul_rn(a.scale_modifier, a.scales[3 * idx + 1]);
     const float s2 = __fmul_rn(a.scale_modifier, a.scales[3 * idx + 2]);
-    const float4 q = reinterpret_cast<const float4*>(a.rotations)[idx];
+    // rotations == nullptr: identity quaternion (GaussianCity's own call pattern,
+    // utils/helpers.py:238-244) -- same arithmetic, so the result is what (1,0,0,0) gives
+    const float4 q = a.rotations != nullptr ? reinterpret_cast<const float4*>(a.rotations)[idx]
+                                            : make_float4(1.f, 0.f, 0.f, 0.f);
     const float r = q.x, x = q.y, y = q.z, z = q.w;
     // R columns (GLM column-major constructor order)
     // (decoded from the reference SASS: shared products are materialised, the other one fused;
@@ -177,23 +180,23 @@ struct StripeSelect {
   uint2 rect;
   uint8_t owner;
 };
-__forceinline__ __device__ StripeSelect stripe_select(unsigned long long packed, const int* __restrict__ bounds,
-                                                      int rank, int count, int grid_y) {
-  const uint32_t x0 = (uint32_t)(packed & 0xFFFu), x1 = (uint32_t)((packed >> 12) & 0xFFFu);
+__forceinline__ __device__ StripeSelect stripe_select(unsigned long long packed, const GcrPreprocessArgs& a) {
+  const int rx0 = (int)(packed & 0xFFFu), rx1 = (int)((packed >> 12) & 0xFFFu);
   const int ry0 = (int)((packed >> 24) & 0xFFFu), ry1 = (int)((packed >> 36) & 0xFFFu);
   const int cr = (int)((packed >> 48) & 0xFFFu);
-  int row0 = 0, row1 = grid_y, owner = 0;
-  if (bounds != nullptr) {
-    row0 = bounds[rank];
-    row1 = bounds[rank + 1];
-    for (int r = 1; r < count; ++r)
-      if (cr >= bounds[r]) owner = r;
+  int row0 = a.win_row0, row1 = a.win_row1, owner = 0;
+  if (a.stripe_bounds != nullptr) {
+    row0 = max(row0, a.stripe_bounds[a.shard_rank]);
+    row1 = min(row1, a.stripe_bounds[a.shard_rank + 1]);
+    for (int r = 1; r < a.shard_count; ++r)
+      if (cr >= a.stripe_bounds[r]) owner = r;
   }
+  const int x0 = max(rx0, a.win_col0), x1 = min(rx1, a.win_col1);
   const int y0 = max(ry0, row0), y1 = min(ry1, row1);
   StripeSelect o;
   o.owner = (uint8_t)owner;
-  o.tiles = y1 > y0 ? (x1 - x0) * (uint32_t)(y1 - y0) : 0u;
-  o.rect = make_uint2(x0 | ((uint32_t)y0 << 16), (x1 - x0) | ((uint32_t)(y1 - y0) << 16));
+  o.tiles = (y1 > y0 && x1 > x0) ? (uint32_t)(x1 - x0) * (uint32_t)(y1 - y0) : 0u;
+  o.rect = make_uint2((uint32_t)x0 | ((uint32_t)y0 << 16), (uint32_t)(x1 - x0) | ((uint32_t)(y1 - y0) << 16));
   return o;
 }
 
@@ -375,14 +378,14 @@ project_kernel(GcrPreprocessArgs a) {
         const uint32_t w = g.rmax.x - g.rmin.x;
         for (uint32_t r = g.rmin.y; r < g.rmax.y; ++r) atomicAdd(use_smem ? &hist[r] : &a.row_hist[r], w);
       } else {
-        const StripeSelect sel = stripe_select(packed, a.stripe_bounds, a.shard_rank, a.shard_count, a.grid_y);
+        const StripeSelect sel = stripe_select(packed, a);
         owner_out = sel.owner;
         tiles = sel.tiles;
         rendered = tiles != 0;
         if (rendered) a.rects[idx] = sel.rect;
       }
       if (rendered) {
-        const float opacity = a.opacities[idx];
+        const float opacity = a.opacities != nullptr ? a.opacities[idx] : 1.0f;   // nullptr: opaque
         GcrRecord* rec = a.records + idx;
         rec->q0 = make_float4(g.pix_x, g.pix_y, g.conic_x, g.conic_y);
         // cull threshold 2*ln(255*opacity): a pixel can only reach alpha >= 1/255 when
@@ -442,57 +445,75 @@ project_kernel(GcrPreprocessArgs a) {
 // coefficients and evaluate the colour, with full warps.  Index order matters: the same
 // coefficient rows fetched in depth order run at a quarter of the bandwidth (measured, DRAM page
 // locality: profiles/r02_*).
+constexpr int kSelItems = 4;                      // Gaussians per thread and chunk
+constexpr int kSelChunk = 256 * kSelItems;        // 1024: four independent loads in flight per thread
+
 template <bool kHasSH>
 __global__ void __launch_bounds__(256, 3)
 stripe_select_kernel(GcrPreprocessArgs a) {
-  __shared__ uint16_t list[256];
-  __shared__ uint32_t wcount[8];
+  __shared__ uint16_t list[kSelChunk];
+  __shared__ uint32_t wcount[kSelItems][8];
   __shared__ uint32_t s_sum;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_sum = 0;
   __syncthreads();
   uint32_t my_tiles = 0;
-  const int nchunks = (a.P + 255) / 256;
+  const int nchunks = (a.P + kSelChunk - 1) / kSelChunk;
   for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {   // block-uniform trip count
-    const int base = chunk * 256;
-    const int idx = base + tid;
-    uint32_t tiles = 0;
-    if (idx < a.P) {
-      const unsigned long long packed = a.packed_rects[idx];
-      uint8_t owner_out = GCR_NO_OWNER;
-      if (packed != 0ull) {
-        const StripeSelect sel = stripe_select(packed, a.stripe_bounds, a.shard_rank, a.shard_count, a.grid_y);
-        owner_out = sel.owner;
-        tiles = sel.tiles;
-        if (tiles != 0) a.rects[idx] = sel.rect;
-        else a.depth_keys[idx] = 0xFFFFFFFFu;   // visible, but not in this rank's stripe
+    const int base = chunk * kSelChunk;
+    unsigned long long packed[kSelItems];
+#pragma unroll
+    for (int k = 0; k < kSelItems; ++k) {
+      const int idx = base + k * 256 + tid;
+      packed[k] = idx < a.P ? a.packed_rects[idx] : 0ull;
+    }
+    bool need[kSelItems];
+    unsigned bal[kSelItems];
+#pragma unroll
+    for (int k = 0; k < kSelItems; ++k) {
+      const int idx = base + k * 256 + tid;
+      uint32_t tiles = 0;
+      if (idx < a.P) {
+        uint8_t owner_out = GCR_NO_OWNER;
+        if (packed[k] != 0ull) {
+          const StripeSelect sel = stripe_select(packed[k], a);
+          owner_out = sel.owner;
+          tiles = sel.tiles;
+          if (tiles != 0) a.rects[idx] = sel.rect;
+          else a.depth_keys[idx] = 0xFFFFFFFFu;   // visible, but not in this rank's stripe
+        }
+        a.tiles_touched[idx] = tiles;
+        a.owner[idx] = owner_out;
+        my_tiles += tiles;
       }
-      a.tiles_touched[idx] = tiles;
-      a.owner[idx] = owner_out;
-      my_tiles += tiles;
+      need[k] = tiles != 0;
+      bal[k] = __ballot_sync(0xffffffffu, need[k]);
+      if (kHasSH && lane == 0) wcount[k][warp] = __popc(bal[k]);
     }
     if (kHasSH) {
-      const bool need = tiles != 0;
-      const unsigned bal = __ballot_sync(0xffffffffu, need);
-      if (lane == 0) wcount[warp] = __popc(bal);
       __syncthreads();
-      uint32_t before = 0, count = 0;
+      // positions in index order: sub-chunk k, then warp, then lane
+      uint32_t count = 0;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) {
-        const uint32_t c = wcount[w];
-        if (w < warp) before += c;
-        count += c;
+      for (int k = 0; k < kSelItems; ++k) {
+        uint32_t before = count;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+          const uint32_t c = wcount[k][w];
+          if (w < warp) before += c;
+          count += c;
+        }
+        if (need[k]) list[before + __popc(bal[k] & ((1u << lane) - 1))] = (uint16_t)(k * 256 + tid);
       }
-      if (need) list[before + __popc(bal & ((1u << lane) - 1))] = (uint16_t)tid;
       __syncthreads();
-      if ((uint32_t)tid < count) {
-        const int g = base + (int)list[tid];
+      for (uint32_t j = tid; j < count; j += 256) {
+        const int g = base + (int)list[j];
         float cr, cg, cb;
         a.clamped[g] = gcr_sh_colour(a, g, a.means3D[3 * g + 0], a.means3D[3 * g + 1], a.means3D[3 * g + 2],
                                      cr, cg, cb);
         a.records[g].q2 = make_float4(cr, cg, cb, 0.f);
       }
-      // list / wcount are rewritten only after the next chunk's first barrier
+      __syncthreads();   // list / wcount are rewritten by the next chunk
     }
   }
   const uint32_t wsum = __reduce_add_sync(0xffffffffu, my_tiles);
@@ -568,8 +589,10 @@ cudaError_t gcr_launch_project(const GcrPreprocessArgs& a, bool deferred, cudaSt
 
 cudaError_t gcr_launch_stripe_select(const GcrPreprocessArgs& a, cudaStream_t stream) {
   if (a.P <= 0) return cudaSuccess;
-  if (a.colors_precomp == nullptr) stripe_select_kernel<true><<<persistent_grid(a.P, 3 * 4), 256, 0, stream>>>(a);
-  else stripe_select_kernel<false><<<persistent_grid(a.P, 8), 256, 0, stream>>>(a);
+  const int chunks = (a.P + kSelChunk - 1) / kSelChunk;
+  const unsigned grid = (unsigned)(chunks < 148 * 12 ? chunks : 148 * 12);
+  if (a.colors_precomp == nullptr) stripe_select_kernel<true><<<grid, 256, 0, stream>>>(a);
+  else stripe_select_kernel<false><<<grid, 256, 0, stream>>>(a);
   return cudaGetLastError();
 }
 

@@ -198,6 +198,81 @@ def mark_visible(means3D, viewmatrix, projmatrix):
     return present
 
 
+# ---- crop folded into the rasterizer + GaussianCity's constant attributes (adapter.py) ----
+def rasterize_gaussians_window(background, means3D, colors, opacity, scales, rotations, scale_modifier,
+                               viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width,
+                               window, debug=False):
+    """colors_precomp path of rasterize_gaussians restricted to the pixel window (x, y, w, h) of the
+    image_height x image_width frame: -> (num_rendered, color[3,h,w], radii, geom, binning, img).
+    opacity=None renders every Gaussian opaque, rotations=None uses the identity rotation."""
+    lib = _cabi.lib()
+    device = means3D.device
+    if not means3D.is_cuda:
+        raise RuntimeError("means3D must be a CUDA tensor (there is no CPU path)")
+    P, H, W = int(means3D.size(0)), int(image_height), int(image_width)
+    x, y, w, h = (int(v) for v in window)
+    with torch.cuda.device(device):
+        out_color = (torch.empty if P != 0 else torch.zeros)((NUM_CHANNELS, h, w), dtype=torch.float32, device=device)
+        radii = torch.zeros((P,), dtype=torch.int32, device=device)
+        geom, binning, img = _Allocator(device), _Allocator(device), _Allocator(device)
+        rendered = 0
+        if P != 0:
+            background = _prep(background, "background", device)
+            means3D = _prep(means3D, "means3D", device)
+            colors = _prep(colors, "colors_precomp", device)
+            opacity = _prep(opacity, "opacity", device)
+            scales = _prep(scales, "scales", device)
+            rotations = _prep(rotations, "rotations", device, align=16)
+            viewmatrix = _prep(viewmatrix, "viewmatrix", device)
+            projmatrix = _prep(projmatrix, "projmatrix", device)
+            rc = lib.gcr_rasterizer_forward_window(
+                geom.cb, None, binning.cb, None, img.cb, None, P, 0, 0, _ptr(background), W, H,
+                _ptr(means3D), None, _ptr(colors), _ptr(opacity), _ptr(scales), float(scale_modifier),
+                _ptr(rotations), None, _ptr(viewmatrix), _ptr(projmatrix), None, float(tan_fovx),
+                float(tan_fovy), 0, _ptr(out_color), _ptr(radii), int(bool(debug)), x, y, w, h,
+                _stream_ptr(device))
+            rendered = _cabi.check(rc, "rasterize_gaussians_window")
+    return rendered, out_color, radii, geom.take(), binning.take(), img.take()
+
+
+def rasterize_gaussians_backward_window(background, means3D, radii, scales, rotations, scale_modifier,
+                                        viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width,
+                                        window, dL_dout_color, geomBuffer, R, binningBuffer, imageBuffer,
+                                        want_opacity=False, debug=False):
+    """-> (dL_dmeans3D[P,3], dL_dcolors[P,3], dL_dscales[P,3], dL_dopacity[P,1] or None,
+    dL_drotations[P,4] or None, dL_dmeans2D[P,3]); dL_dout_color is [3,h,w]."""
+    lib = _cabi.lib()
+    device = means3D.device
+    P = int(means3D.size(0))
+    x, y, w, h = (int(v) for v in window)
+    opts = dict(dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        alloc = torch.empty if P != 0 else torch.zeros
+        dL_dmeans3D, dL_dmeans2D, dL_dcolors = alloc((P, 3), **opts), alloc((P, 3), **opts), alloc((P, 3), **opts)
+        dL_dcov3D, dL_dscales = alloc((P, 6), **opts), alloc((P, 3), **opts)
+        dL_dopacity = alloc((P, 1), **opts) if want_opacity else None
+        dL_drot = alloc((P, 4), **opts) if rotations is not None and rotations.numel() else None
+        if P != 0:
+            background = _prep(background, "background", device)
+            means3D = _prep(means3D, "means3D", device)
+            scales = _prep(scales, "scales", device)
+            rotations = _prep(rotations, "rotations", device, align=16)
+            viewmatrix = _prep(viewmatrix, "viewmatrix", device)
+            projmatrix = _prep(projmatrix, "projmatrix", device)
+            dL_dout_color = _prep(dL_dout_color, "dL_dout_color", device)
+            rc = lib.gcr_rasterizer_backward_window(
+                P, 0, 0, int(R), _ptr(background), int(image_width), int(image_height), _ptr(means3D), None,
+                None, _ptr(scales), float(scale_modifier), _ptr(rotations), None, _ptr(viewmatrix),
+                _ptr(projmatrix), None, float(tan_fovx), float(tan_fovy), _ptr(radii.contiguous()),
+                ctypes.c_void_p(geomBuffer.data_ptr()),
+                ctypes.c_void_p(binningBuffer.data_ptr()) if binningBuffer.numel() else None,
+                ctypes.c_void_p(imageBuffer.data_ptr()), _ptr(dL_dout_color), _ptr(dL_dmeans2D), None,
+                _ptr(dL_dopacity), _ptr(dL_dcolors), _ptr(dL_dmeans3D), _ptr(dL_dcov3D), None,
+                _ptr(dL_dscales), _ptr(dL_drot), int(bool(debug)), x, y, w, h, _stream_ptr(device))
+            _cabi.check(rc, "rasterize_gaussians_backward_window")
+    return dL_dmeans3D, dL_dcolors, dL_dscales, dL_dopacity, dL_drot, dL_dmeans2D
+
+
 # ---- tile-row stripes of a multi-GPU frame (gaussiancity_b200.sharding) -------------------------
 def stripe_partition(means3D, scales, rotations, scale_modifier, viewmatrix, projmatrix, tan_fovx,
                      tan_fovy, image_height, image_width, shard_count, workspace, bounds_out,
@@ -268,7 +343,7 @@ def rasterize_gaussians_backward_blend(background, P, R, dL_dout_color, geomBuff
                 int(P), int(R), _ptr(background), W, H, ctypes.c_void_p(geomBuffer.data_ptr()),
                 ctypes.c_void_p(binningBuffer.data_ptr()) if binningBuffer.numel() else None,
                 ctypes.c_void_p(imageBuffer.data_ptr()), _ptr(dL_dout_color), ptrs, n_acc, zero_first,
-                int(bool(remote_scalar)), int(bool(debug)), int(shard_rank), int(shard_count),
+                int(bool(remote_scalar)), int(bool(debug)), int(shard_rank), int(shard_count), None,
                 _stream_ptr(device))
             _cabi.check(rc, "rasterize_gaussians_backward_blend")
     return grad_acc

@@ -92,6 +92,40 @@ GCR_API int gcr_rasterizer_forward_striped(gcr_alloc_fn geometryBuffer, void* ge
                            int shard_rank, int shard_count, const int* stripe_bounds,
                            int balanced, void* cuda_stream);
 
+/* Crop folded into the rasterizer (replaces render-then-slice in
+ * utils/helpers.py:250-270).  Only the tiles that intersect the pixel window [win_x, win_x+win_w) x
+ * [win_y, win_y+win_h) are binned and blended; out_color is [3, win_h, win_w].  The tile grid, the
+ * camera and every Gaussian's tile rect are those of the FULL width x height frame, so each pixel of
+ * the window has exactly the value the full render would give it.  num_rendered counts the window's
+ * tile instances.  Two more conveniences for GaussianCity's call pattern, valid in every forward:
+ * opacities == NULL renders every Gaussian opaque (opacity 1) and rotations == NULL (with scales)
+ * uses the identity rotation -- bit-identical to passing ones / (1,0,0,0), without materialising
+ * them (utils/helpers.py:226-247).  gcr_rasterizer_backward_window is the matching backward:
+ * dL_dpix is [3, win_h, win_w]; dL_dopacity / dL_drot may be NULL. */
+GCR_API int gcr_rasterizer_forward_window(gcr_alloc_fn geometryBuffer, void* geometry_ctx,
+                           gcr_alloc_fn binningBuffer, void* binning_ctx,
+                           gcr_alloc_fn imageBuffer, void* image_ctx,
+                           int P, int D, int M, const float* background, int width, int height,
+                           const float* means3D, const float* shs, const float* colors_precomp,
+                           const float* opacities, const float* scales, float scale_modifier,
+                           const float* rotations, const float* cov3D_precomp,
+                           const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+                           float tan_fovx, float tan_fovy, int prefiltered, float* out_color,
+                           int* radii, int debug,
+                           int win_x, int win_y, int win_w, int win_h, void* cuda_stream);
+GCR_API int gcr_rasterizer_backward_window(int P, int D, int M, int R, const float* background, int width,
+                            int height, const float* means3D, const float* shs,
+                            const float* colors_precomp, const float* scales,
+                            float scale_modifier, const float* rotations,
+                            const float* cov3D_precomp, const float* viewmatrix,
+                            const float* projmatrix, const float* campos, float tan_fovx,
+                            float tan_fovy, const int* radii, char* geom_buffer,
+                            char* binning_buffer, char* image_buffer, const float* dL_dpix,
+                            float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
+                            float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh,
+                            float* dL_dscale, float* dL_drot, int debug,
+                            int win_x, int win_y, int win_w, int win_h, void* cuda_stream);
+
 /* Returns 0, or < 0 on error.  Every element of every gradient array is written (zeros for
  * culled Gaussians): callers need not pre-zero them.  dL_dconic ([P,2,2]), dL_dsh, dL_dscale,
  * dL_drot may be NULL.  Single-stripe frames only (shard_count must be 1): a striped frame goes
@@ -123,7 +157,8 @@ GCR_API int gcr_rasterizer_backward(int P, int D, int M, int R, const float* bac
  *                                  the rank that OWNS it (the stripe holding its centre row), over
  *                                  NVLink, inside the blend kernel.  Owners then need only a
  *                                  gcr_peer_barrier before _geometry -- no reduce-scatter.
- * The stripe bounds of the forward travel inside geom_buffer.
+ * The stripe bounds of the forward travel inside geom_buffer.  window: NULL, or a HOST array
+ * {x, y, w, h} = the pixel window of a gcr_rasterizer_forward_window frame (dL_dpix is then [3,h,w]).
  * zero_first != 0 zeroes accumulators[n == 1 ? 0 : shard_rank] before accumulating (not wanted for
  * peer-shared accumulators: _geometry(clear_accumulator) leaves them zeroed instead).
  *
@@ -135,7 +170,8 @@ GCR_API int gcr_rasterizer_backward_blend(int P, int R, const float* background,
                                   char* geom_buffer, char* binning_buffer, char* image_buffer,
                                   const float* dL_dpix, float* const* accumulators,
                                   int n_accumulators, int zero_first, int remote_scalar_atomics,
-                                  int debug, int shard_rank, int shard_count, void* cuda_stream);
+                                  int debug, int shard_rank, int shard_count, const int* window,
+                                  void* cuda_stream);
 GCR_API int gcr_rasterizer_backward_geometry(int P, int D, int M, const float* means3D, const float* shs,
                                      const float* scales, float scale_modifier,
                                      const float* rotations, const float* cov3D_precomp,

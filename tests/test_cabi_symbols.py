@@ -80,6 +80,7 @@ def test_argument_validation_returns_errors_without_touching_the_device(built_li
              (dict(shs=None, colors=None), "SHs or precomputed"), (dict(scales=None), "scale/rotation"),
              (dict(D=3, M=4), "SH degree"), (dict(rot=C.c_void_p(0x10004)), "16-byte aligned"),
              (dict(M=16, D=3, shs=C.c_void_p(0x10010)), "32-byte aligned"), (dict(means=None), "must not be NULL"),
+             (dict(W=70000 * 16), "65520"),
              (dict(M=25, D=3), "at most 16 SH"), (dict(shard_rank=0, shard_count=17), "shard")]
     for kw, msg in cases:
         assert fwd(**kw) < 0, kw
@@ -93,7 +94,7 @@ def test_argument_validation_returns_errors_without_touching_the_device(built_li
         arr = (C.c_void_p * max(1, len(a["accs"])))(*a["accs"]) if a["accs"] is not None else None
         return l.gcr_rasterizer_backward_blend(a["P"], a["R"], a["bg"], a["W"], a["H"], a["geom"], a["binning"],
                                                a["img"], a["dpix"], arr, len(a["accs"] or []), a["zero"], 0, 0,
-                                               a["rank"], a["count"], None)
+                                               a["rank"], a["count"], None, None)
 
     assert blend(P=0) == 0
     for kw, msg in [(dict(accs=None), "accumulators"), (dict(accs=[0x20000, 0x30000]), "one per rank"),

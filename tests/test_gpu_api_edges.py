@@ -157,6 +157,128 @@ def test_native_module_matches_ctypes_binding(built_lib, cuda_device):
                                    torch.zeros(30_000, 4, 3, device=cuda_device), 3, s.campos, False, False)
 
 
+@pytest.mark.parametrize("flip_lr,crop", [(True, dict(x=160, y=46, w=640, h=448)), (False, dict(x=7, y=3, w=333, h=210)),
+                                          (True, None)], ids=["train_crop", "odd_crop_noflip", "full_frame"])
+def test_adapter_fusion_matches_reference_adapter_and_crop(built_lib, cuda_device, flip_lr, crop):
+    """generator attributes in, cropped image out -- against the reference's own
+    sequence (utils/helpers.py:226-270: cat to [N,14] with ones / identity quaternions, wrapper
+    render of the full 960x540 frame through the unmodified reference extension, flip, slice).
+    Image bit-exact inside the window; gradients of xyz / scales / rgb <= 1e-4."""
+    from gaussiancity_b200 import adapter
+    ref = refext.load_reference_ext()
+    assert ref is not None, "oracle/_ref is not built"
+    pts, cam_pos, cam_quat = city_points(30_000, seed=9, device=cuda_device)
+    xyz, scales, rgb = (pts[:, 0:3].contiguous(), pts[:, 4:7].contiguous(), pts[:, 11:14].contiguous())
+    wrap = g.GaussianRasterizerWrapper(CITY_K, CITY_SENSOR, flip_lr=flip_lr, device=cuda_device)
+    st = wrap._get_gaussian_rasterization_settings(cam_pos, cam_quat)
+    H, W = 540, 960
+    # ---- reference sequence ----
+    ones = torch.ones(xyz.shape[0], 1, device=cuda_device)
+    quat = torch.cat([ones, torch.zeros(xyz.shape[0], 3, device=cuda_device)], dim=1)
+    e = torch.Tensor([])
+    fargs = (st.bg, xyz, rgb, ones, scales, quat, 1.0, e, st.view_matrix, st.proj_matrix, st.tanfovx, st.tanfovy,
+             H, W, e, 0, st.campos, False, False)
+    R_ref, col_ref, rad_ref, geom_ref, bin_ref, img_ref = ref.rasterize_gaussians(*fargs)
+    out_ref = torch.flip(col_ref, dims=[2]) if flip_lr else col_ref
+    c = crop if crop is not None else dict(x=0, y=0, w=W, h=H)
+    out_ref_c = out_ref[:, c["y"]:c["y"] + c["h"], c["x"]:c["x"] + c["w"]]
+    # ---- fused adapter ----
+    leaves = [t.clone().requires_grad_(True) for t in (xyz, scales, rgb)]
+    out = adapter.render_gaussian_points(leaves[0], leaves[1], leaves[2], wrap, cam_pos, cam_quat, crop=crop)
+    assert out.shape == out_ref_c.shape
+    assert torch.equal(out, out_ref_c), f"{(out != out_ref_c).sum().item()} pixels differ inside the window"
+    G = torch.randn(out.shape, generator=torch.Generator().manual_seed(3)).to(cuda_device)
+    (out * G).sum().backward()
+    # reference gradient: the window's cotangent zero-padded to the full (flipped back) frame
+    Gfull = torch.zeros(3, H, W, device=cuda_device)
+    Gfull[:, c["y"]:c["y"] + c["h"], c["x"]:c["x"] + c["w"]] = G
+    if flip_lr:
+        Gfull = torch.flip(Gfull, dims=[2]).contiguous()
+    gr = ref.rasterize_gaussians_backward(st.bg, xyz, rad_ref, rgb, scales, quat, 1.0, e, st.view_matrix,
+                                          st.proj_matrix, st.tanfovx, st.tanfovy, Gfull, e, 0, st.campos, geom_ref,
+                                          R_ref, bin_ref, img_ref, False)
+    rel = lambda a, b: (a.double() - b.double()).norm().item() / max(b.double().norm().item(), 1e-30)
+    assert rel(leaves[0].grad, gr[3]) <= 1e-4 and rel(leaves[1].grad, gr[6]) <= 1e-4 and rel(leaves[2].grad, gr[1]) <= 1e-4
+    # batched helper == the reference helpers' semantics (xyz offsets, scale factors, opacity given)
+    if crop is not None and flip_lr:
+        attrs = dict(rgb=rgb[None], xyz=torch.zeros_like(xyz)[None] + 0.25, scale=torch.full_like(scales, 1.5)[None],
+                     opacity=torch.full((1, xyz.shape[0], 1), 0.7, device=cuda_device))
+        imgs = adapter.get_gaussian_rasterization_fused(xyz[None], scales[None], attrs, wrap, [cam_pos], [cam_quat], [crop])
+        fa = (st.bg, xyz + 0.25, rgb, attrs["opacity"][0], scales * 1.5, quat, 1.0, e, st.view_matrix, st.proj_matrix,
+              st.tanfovx, st.tanfovy, H, W, e, 0, st.campos, False, False)
+        col2 = torch.flip(ref.rasterize_gaussians(*fa)[1], dims=[2])
+        assert torch.equal(imgs[0], col2[:, c["y"]:c["y"] + c["h"], c["x"]:c["x"] + c["w"]])
+
+
+def _reference_wrapper_class():
+    """The reference's own GaussianRasterizerWrapper (unmodified DGR/__init__.py, staged into
+    baseline/_ref by oracle/build_ref.py) on top of the reference extension, or None."""
+    import importlib.util
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.path.join(root, "baseline", "_ref", "GaussianCity", "extensions", "diff_gaussian_rasterization", "__init__.py")
+    if not os.path.exists(path) or refext.load_reference_ext() is None:
+        return None
+    spec = importlib.util.spec_from_file_location("_ref_dgr_python", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)        # imports diff_gaussian_rasterization_ext = the reference .so (oracle/_ref)
+    assert "oracle/_ref" in sys.modules["diff_gaussian_rasterization_ext"].__file__
+    return mod.GaussianRasterizerWrapper
+
+
+def test_fast_camera_wrapper_matches_reference_wrapper(built_lib, cuda_device):
+    """the host-side camera path (one packed upload per new pose + LRU cache) against
+    the reference wrapper's device matmul / inverse sequence: settings <= 1e-6, view matrix bit for
+    bit, the rendered frame <= 1e-4 -- and against the reference's own wrapper class over the
+    reference extension when its staged copy is present."""
+    pts, cam_pos, cam_quat = city_points(40_000, seed=2, device=cuda_device)
+    fast = g.GaussianRasterizerWrapper(CITY_K, CITY_SENSOR, device=cuda_device, fast_camera=True)
+    slow = g.GaussianRasterizerWrapper(CITY_K, CITY_SENSOR, device=cuda_device, fast_camera=False)
+    sf = fast._get_gaussian_rasterization_settings(cam_pos, cam_quat)
+    ss = slow._get_gaussian_rasterization_settings(cam_pos, cam_quat)
+    assert torch.equal(sf.view_matrix, ss.view_matrix)
+    assert (sf.proj_matrix - ss.proj_matrix).abs().max().item() <= 1e-6 * ss.proj_matrix.abs().max().item()
+    assert (sf.campos - ss.campos).abs().max().item() <= 1e-3      # ~600 units away: 1e-6 relative
+    a, b = fast(pts, cam_pos, cam_quat), slow(pts, cam_pos, cam_quat)
+    assert (a - b).abs().max().item() <= 1e-4 and (a != b).float().mean().item() < 1e-2
+    assert fast._get_gaussian_rasterization_settings(cam_pos, cam_quat).view_matrix is sf.view_matrix   # cache hit
+    Ref = _reference_wrapper_class()
+    if Ref is not None:
+        r = Ref(CITY_K, CITY_SENSOR, device=cuda_device)(pts, cam_pos, cam_quat)
+        assert torch.equal(b, r), "mirror of the reference wrapper differs from the reference wrapper itself"
+        assert (a - r).abs().max().item() <= 1e-4
+
+
+def test_forward_only_frame_loop_matches_wrapper(built_lib, cuda_device):
+    """the forward-only renderer (persistent buffers, SoA attributes, NULL opacity /
+    rotation, optional crop) produces the wrapper's frames bit for bit, frame after frame with
+    changing point counts and poses; render_video hands every frame to the sink, in order, as the
+    uint8 image utils.helpers.tensor_to_image would give."""
+    from gaussiancity_b200.inference import FrameRenderer
+    wrap = g.GaussianRasterizerWrapper(CITY_K, CITY_SENSOR, device=cuda_device, fast_camera=True)
+    fr = FrameRenderer(wrap)
+    frames, expect = [], []
+    for i, n in enumerate([30_000, 8_000, 50_000, 50_000]):
+        pts, cam_pos, cam_quat = city_points(n, seed=20 + i, device=cuda_device)
+        cam_pos = cam_pos + np.array([3.0 * i, -2.0 * i, 1.0 * i])
+        expect.append(wrap(pts, cam_pos, cam_quat))
+        frames.append(dict(xyz=pts[:, 0:3], scales=pts[:, 4:7], rgb=pts[:, 11:14], cam_position=cam_pos,
+                           cam_quaternion=cam_quat))
+    for f, e in zip(frames, expect):
+        img = fr.render(f["xyz"], f["scales"], f["rgb"], f["cam_position"], f["cam_quaternion"])
+        assert torch.equal(img, e)
+        crop = dict(x=100, y=40, w=640, h=448)
+        imgc = fr.render(f["xyz"], f["scales"], f["rgb"], f["cam_position"], f["cam_quaternion"], crop=crop)
+        assert torch.equal(imgc, e[:, 40:488, 100:740])
+    got = {}
+    n = fr.render_video(frames, lambda i, arr: got.__setitem__(i, arr.copy()))
+    assert n == 4 and sorted(got) == [0, 1, 2, 3]
+    for i, e in enumerate(expect):
+        u8 = ((e * 0.5 + 0.5).clamp(0, 1) * 255.0).round().to(torch.uint8).permute(1, 2, 0).cpu().numpy()
+        assert got[i].shape == (540, 960, 3) and np.array_equal(got[i], u8)
+
+
 def test_empty_and_fully_culled_inputs(built_lib, cuda_device):
     s = uniform_scene(64, 48, 40, seed=1, device=cuda_device, bg=(0.5, 0.25, 0.125))
     e = torch.Tensor([])

@@ -79,6 +79,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--points", type=int, default=16384)
+    ap.add_argument("--profile", action="store_true", help="host + device time of the rasterizer calls inside the step")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -125,6 +126,7 @@ def main():
     crp = [dict(x=160, y=46, w=640, h=448)]
     cam_pos_b, cam_quat_b = [np.asarray(cam_pos, dtype=np.float32)], [np.asarray(cam_quat, dtype=np.float32)]
 
+    ours = None
     if args.arm == "ours_wrapper":
         import gaussiancity_b200 as ours
         gr = ours.GaussianRasterizerWrapper(CITY_K, CITY_SENSOR, device=dev, fast_camera=True)
@@ -132,6 +134,26 @@ def main():
         gr = dgr.GaussianRasterizerWrapper(K=CITY_K, sensor_size=CITY_SENSOR, flip_ud=False, device=dev)
     l1 = torch.nn.L1Loss()
     losses = []
+    prof = {"fwd_host_ms": 0.0, "bwd_host_ms": 0.0, "calls": 0, "events": []}
+    if args.profile:
+        targets = [native_ext]
+        if args.arm == "ours_wrapper":
+            targets = [ours.dgr_ext]
+        for mod in targets:
+            for name, key in (("rasterize_gaussians", "fwd"), ("rasterize_gaussians_backward", "bwd")):
+                fn = getattr(mod, name)
+
+                def wrapped(*a, _fn=fn, _key=key):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    t = time.perf_counter()
+                    out = _fn(*a)
+                    prof[_key + "_host_ms"] += (time.perf_counter() - t) * 1e3
+                    e1.record()
+                    prof["events"].append((_key, e0, e1))
+                    prof["calls"] += 1
+                    return out
+                setattr(mod, name, wrapped)
 
     def step(i):
         torch.manual_seed(5000 + i)      # utils.helpers.get_z draws from the global generator
@@ -146,7 +168,7 @@ def main():
         return loss
 
     for i in range(args.warmup):
-        losses.append(float(step(i)))
+        losses.append(float(step(i).detach()))
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -154,12 +176,22 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.warmup, args.warmup + args.steps):
-        losses.append(step(i))
+        losses.append(step(i).detach())
     e1.record()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     losses = [float(x) for x in losses]
     ms = e0.elapsed_time(e1) / args.steps
+    raster = None
+    if args.profile:
+        n = max(1, prof["calls"] // 2)
+        dev_ms = {"fwd": 0.0, "bwd": 0.0}
+        for key, a, b in prof["events"]:
+            dev_ms[key] += a.elapsed_time(b)
+        raster = {"calls_fwd": n, "fwd_host_ms_per_call": prof["fwd_host_ms"] / n, "bwd_host_ms_per_call": prof["bwd_host_ms"] / n,
+                  "fwd_stream_ms_per_call": dev_ms["fwd"] / n, "bwd_stream_ms_per_call": dev_ms["bwd"] / n,
+                  "note": "host = wall time inside the native call; stream = CUDA-event interval around it on the "
+                          "launching stream (includes waiting for earlier generator kernels only if the call synchronises)"}
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -169,6 +201,7 @@ def main():
                           "points": int(N), "render": "960x540", "crop": "640x448", "steps": args.steps,
                           "ms_per_step": ms, "it_per_s_per_rank": 1000.0 / ms, "it_per_s_total": world * 1000.0 / ms,
                           "wall_ms_per_step": wall * 1e3 / args.steps, "losses": losses,
+                          "rasterizer": raster,
                           "rasterizer_module": native_ext.__file__.replace(ROOT + "/", ""),
                           "dgr_python": dgr.__file__.replace(ref_root, "<reference>"),
                           "generator": "reference models/generator.py, ENCODER=None POS_EMD=SIN_COS Z_DIM=256 PTV3 off"}))

@@ -19,5 +19,11 @@ for (P, W, H, deg, use_sh, sig) in [(3000, 96, 80, 3, True, (0.5, 4.0)), (1500, 
         ext.rasterize_gaussians_backward_geometry(s.means3D, rk, s.scales, s.rotations, 1.0, e, s.view_matrix,
             s.proj_matrix, s.tanfovx, s.tanfovy, H, W, s.shs if s.shs is not None else e, s.sh_degree, s.campos,
             gk, acc, shard_rank=k, striped=True)
+    if not use_sh:   # crop folded into the rasterizer, NULL opacity / rotation (adapter path)
+        win = (3, 5, W - 9, H - 7)
+        Rw, cw, rw, gw, bw, iw = ext.rasterize_gaussians_window(s.bg, s.means3D, s.colors_precomp, None, s.scales, None, 1.0,
+                                                                s.view_matrix, s.proj_matrix, s.tanfovx, s.tanfovy, H, W, win)
+        ext.rasterize_gaussians_backward_window(s.bg, s.means3D, rw, s.scales, None, 1.0, s.view_matrix, s.proj_matrix,
+                                                s.tanfovx, s.tanfovy, H, W, win, torch.ones_like(cw), gw, Rw, bw, iw)
     torch.cuda.synchronize()
     print("ok", P, W, H, "R", R, float(color.sum()), float(grads[3].abs().sum()))
