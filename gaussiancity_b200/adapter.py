@@ -20,16 +20,33 @@ from . import ext
 __all__ = ["render_gaussian_points", "get_gaussian_rasterization_fused"]
 
 
+def _native():
+    """The native torch module when it is built (same C ABI underneath, ~10x less host time per call
+    than ctypes -- this path exists for GaussianCity's launch-bound <= 16 k-point frames)."""
+    try:
+        from .compat import diff_gaussian_rasterization_ext as m
+        return m if hasattr(m, "rasterize_gaussians_window") else None
+    except ImportError:
+        return None
+
+
 class _WindowRasterize(torch.autograd.Function):
     @staticmethod
     def forward(ctx, xyz, scales, rgb, opacity, rotations, settings, window):
         rs = settings
-        R, color, radii, geom, binning, img = ext.rasterize_gaussians_window(
-            rs.bg, xyz, rgb, opacity, scales, rotations, rs.scale_modifier, rs.view_matrix, rs.proj_matrix,
-            rs.tanfovx, rs.tanfovy, rs.img_h, rs.img_w, window, rs.debug)
+        nat = _native()
+        e = torch.Tensor([])
+        if nat is not None:
+            R, color, radii, geom, binning, img = nat.rasterize_gaussians_window(
+                rs.bg, xyz, rgb, opacity if opacity is not None else e, scales,
+                rotations if rotations is not None else e, rs.scale_modifier, rs.view_matrix, rs.proj_matrix,
+                rs.tanfovx, rs.tanfovy, rs.img_h, rs.img_w, *window, rs.debug)
+        else:
+            R, color, radii, geom, binning, img = ext.rasterize_gaussians_window(
+                rs.bg, xyz, rgb, opacity, scales, rotations, rs.scale_modifier, rs.view_matrix, rs.proj_matrix,
+                rs.tanfovx, rs.tanfovy, rs.img_h, rs.img_w, window, rs.debug)
         ctx.rs, ctx.window, ctx.R = rs, window, R
         ctx.has_opacity, ctx.has_rot = opacity is not None, rotations is not None
-        e = torch.Tensor([])
         ctx.save_for_backward(xyz, scales, rotations if rotations is not None else e, radii, geom, binning, img)
         return color
 
@@ -37,10 +54,19 @@ class _WindowRasterize(torch.autograd.Function):
     def backward(ctx, grad_color):
         rs = ctx.rs
         xyz, scales, rotations, radii, geom, binning, img = ctx.saved_tensors
-        d_xyz, d_rgb, d_scales, d_opacity, d_rot, _ = ext.rasterize_gaussians_backward_window(
-            rs.bg, xyz, radii, scales, rotations if ctx.has_rot else None, rs.scale_modifier, rs.view_matrix,
-            rs.proj_matrix, rs.tanfovx, rs.tanfovy, rs.img_h, rs.img_w, ctx.window, grad_color, geom, ctx.R,
-            binning, img, want_opacity=ctx.has_opacity, debug=rs.debug)
+        nat = _native()
+        if nat is not None:
+            d_xyz, d_rgb, d_scales, d_opacity, d_rot, _ = nat.rasterize_gaussians_backward_window(
+                rs.bg, xyz, radii, scales, rotations, rs.scale_modifier, rs.view_matrix, rs.proj_matrix, rs.tanfovx,
+                rs.tanfovy, rs.img_h, rs.img_w, *ctx.window, grad_color, geom, ctx.R, binning, img, ctx.has_opacity,
+                rs.debug)
+            d_opacity = d_opacity if ctx.has_opacity else None
+            d_rot = d_rot if ctx.has_rot else None
+        else:
+            d_xyz, d_rgb, d_scales, d_opacity, d_rot, _ = ext.rasterize_gaussians_backward_window(
+                rs.bg, xyz, radii, scales, rotations if ctx.has_rot else None, rs.scale_modifier, rs.view_matrix,
+                rs.proj_matrix, rs.tanfovx, rs.tanfovy, rs.img_h, rs.img_w, ctx.window, grad_color, geom, ctx.R,
+                binning, img, want_opacity=ctx.has_opacity, debug=rs.debug)
         return d_xyz, d_scales, d_rgb, d_opacity, d_rot, None, None
 
 

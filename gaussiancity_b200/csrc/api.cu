@@ -132,7 +132,7 @@ struct Carver {
 
 struct GeomLayout {
   size_t keys_a, keys_b, vals_a, vals_b, tiles, records, rects, packed_rects, clamped, owner, offsets, grad_acc,
-      radii, zero_begin, counters, row_hist, sort_ws, emit_ws, zero_end, total;
+      radii, zero_begin, counters, row_hist, select_ws, sort_ws, emit_ws, zero_end, total;
   explicit GeomLayout(size_t P) {
     Carver c;
     keys_a = c.take(4 * P);
@@ -151,6 +151,7 @@ struct GeomLayout {
     // one contiguous block zeroed by a single memset per forward: counters + both workspaces
     counters = zero_begin = c.take(GCR_CNT_WORDS * sizeof(uint32_t));
     row_hist = c.take((4096 + 1) * sizeof(uint32_t));   // instances per tile row (+1: done-CTA ticket)
+    select_ws = c.take(256 + ((P + 1023) / 1024 + 1) * sizeof(unsigned long long));   // ticket | status
     sort_ws = c.take(gcr_sort_workspace_bytes(P));
     emit_ws = c.take(gcr_emit_workspace_bytes(P));
     zero_end = gcr_align_up(c.off, 256);
@@ -322,6 +323,13 @@ int forward_impl(gcr_alloc_fn geometryBuffer, void* geometry_ctx, gcr_alloc_fn b
   pa.packed_rects = reinterpret_cast<unsigned long long*>(gptr + gl.packed_rects);
   pa.row_hist = reinterpret_cast<uint32_t*>(gptr + gl.row_hist);
   pa.stripe_bounds_out = bounds_dev;
+  // balanced stripes: the projection leaves index-ordered depths in the b side of the sort's key
+  // ping-pong; the select stage compacts this stripe's (key, index) pairs into the a side
+  pa.depth_in = keys_b;
+  pa.sorted_init = vals_a;
+  pa.n_vis_out = counters + GCR_CNT_NVIS;
+  pa.select_ticket = reinterpret_cast<uint32_t*>(gptr + gl.select_ws);
+  pa.select_status = reinterpret_cast<unsigned long long*>(gptr + gl.select_ws + 256);
   pa.dbg_cov3D = g_dbg_cov3d;
   g_dbg_cov3d = nullptr;
   prof_mark(ST_PREPROCESS, 0, stream);
@@ -345,9 +353,13 @@ int forward_impl(gcr_alloc_fn geometryBuffer, void* geometry_ctx, gcr_alloc_fn b
 
   // 2. stable depth sort of the Gaussians that touch this stripe (4 passes: result in the a pair)
   prof_mark(ST_DEPTH_SORT, 0, stream);
+  // direct mode: culled Gaussians are dropped (and indices generated) by the sort's first pass;
+  // balanced stripes: the select stage already compacted this stripe's pairs, count on the device
   GCR_LAUNCH("depth sort",
-             gcr_launch_radix_sort(keys_a, vals_a, keys_b, vals_b, (size_t)P, nullptr, 32, true, false,
-                                   counters + GCR_CNT_NVIS, gptr + gl.sort_ws, stream),
+             deferred ? gcr_launch_radix_sort(keys_a, vals_a, keys_b, vals_b, (size_t)P, counters + GCR_CNT_NVIS,
+                                              32, false, false, nullptr, gptr + gl.sort_ws, stream)
+                      : gcr_launch_radix_sort(keys_a, vals_a, keys_b, vals_b, (size_t)P, nullptr, 32, true, false,
+                                              counters + GCR_CNT_NVIS, gptr + gl.sort_ws, stream),
              debug, stream);
   prof_mark(ST_DEPTH_SORT, 1, stream);
   const uint32_t* sorted_gauss = vals_a;

@@ -51,6 +51,11 @@ struct GcrPreprocessArgs {
   unsigned long long* total_tiles;  // zeroed; += sum of tiles_touched (= num_rendered)
   // balanced stripes (deferred mode) / standalone partition
   unsigned long long* packed_rects;  // [P] global rect + centre row, 0 = culled
+  uint32_t* depth_in;                // [P] depth keys in index order (deferred mode: compacted by the select stage
+  uint32_t* sorted_init;             //     into depth_keys / sorted_init = the depth sort's input pairs)
+  uint32_t* n_vis_out;               // number of Gaussians that reach this rank's stripe
+  uint32_t* select_ticket;           // zeroed
+  unsigned long long* select_status; // [ceil(P / 1024)] zeroed
   uint32_t* row_hist;                // [grid_y + 1] zeroed: instances per tile row, +1 = done-CTA ticket
   int* stripe_bounds_out;            // [shard_count + 1]
   float* dbg_cov3D;  // optional [P,6]

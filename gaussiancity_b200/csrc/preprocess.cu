@@ -400,10 +400,11 @@ project_kernel(GcrPreprocessArgs a) {
       }
     }
     a.radii[idx] = radius_out;
-    a.depth_keys[idx] = depth_key;
     if (kDeferred) {
+      a.depth_in[idx] = depth_key;       // compacted into depth_keys by stripe_select_kernel
       a.packed_rects[idx] = packed;
     } else {
+      a.depth_keys[idx] = depth_key;
       a.tiles_touched[idx] = tiles;
       a.owner[idx] = owner_out;
       my_tiles += tiles;
@@ -448,18 +449,30 @@ project_kernel(GcrPreprocessArgs a) {
 constexpr int kSelItems = 4;                      // Gaussians per thread and chunk
 constexpr int kSelChunk = 256 * kSelItems;        // 1024: four independent loads in flight per thread
 
+#define kSelAgg (1ull << 62)
+#define kSelIncl (2ull << 62)
+#define kSelVal ((1ull << 62) - 1ull)
+
 template <bool kHasSH>
 __global__ void __launch_bounds__(256, 3)
 stripe_select_kernel(GcrPreprocessArgs a) {
   __shared__ uint16_t list[kSelChunk];
   __shared__ uint32_t wcount[kSelItems][8];
   __shared__ uint32_t s_sum;
+  __shared__ int s_chunk;
+  __shared__ uint32_t s_excl;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_sum = 0;
-  __syncthreads();
   uint32_t my_tiles = 0;
   const int nchunks = (a.P + kSelChunk - 1) / kSelChunk;
-  for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {   // block-uniform trip count
+  volatile unsigned long long* status = a.select_status;
+  while (true) {
+    // chunks in ticket order: a chunk's predecessors have always started (look-back cannot deadlock)
+    __syncthreads();   // s_chunk / s_excl / list / wcount of the previous chunk are no longer read
+    if (tid == 0) s_chunk = (int)atomicAdd(a.select_ticket, 1u);
+    __syncthreads();
+    const int chunk = s_chunk;
+    if (chunk >= nchunks) break;
     const int base = chunk * kSelChunk;
     unsigned long long packed[kSelItems];
 #pragma unroll
@@ -480,7 +493,6 @@ stripe_select_kernel(GcrPreprocessArgs a) {
           owner_out = sel.owner;
           tiles = sel.tiles;
           if (tiles != 0) a.rects[idx] = sel.rect;
-          else a.depth_keys[idx] = 0xFFFFFFFFu;   // visible, but not in this rank's stripe
         }
         a.tiles_touched[idx] = tiles;
         a.owner[idx] = owner_out;
@@ -488,24 +500,26 @@ stripe_select_kernel(GcrPreprocessArgs a) {
       }
       need[k] = tiles != 0;
       bal[k] = __ballot_sync(0xffffffffu, need[k]);
-      if (kHasSH && lane == 0) wcount[k][warp] = __popc(bal[k]);
+      if (lane == 0) wcount[k][warp] = __popc(bal[k]);
     }
-    if (kHasSH) {
-      __syncthreads();
-      // positions in index order: sub-chunk k, then warp, then lane
-      uint32_t count = 0;
+    __syncthreads();
+    // positions in index order: sub-chunk k, then warp, then lane
+    uint32_t count = 0;
 #pragma unroll
-      for (int k = 0; k < kSelItems; ++k) {
-        uint32_t before = count;
+    for (int k = 0; k < kSelItems; ++k) {
+      uint32_t before = count;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) {
-          const uint32_t c = wcount[k][w];
-          if (w < warp) before += c;
-          count += c;
-        }
-        if (need[k]) list[before + __popc(bal[k] & ((1u << lane) - 1))] = (uint16_t)(k * 256 + tid);
+      for (int w = 0; w < 8; ++w) {
+        const uint32_t c = wcount[k][w];
+        if (w < warp) before += c;
+        count += c;
       }
-      __syncthreads();
+      if (need[k]) list[before + __popc(bal[k] & ((1u << lane) - 1))] = (uint16_t)(k * 256 + tid);
+    }
+    // publish this chunk's member count before the colour work: successors look back late
+    if (tid == 0) status[chunk] = (chunk == 0 ? kSelIncl : kSelAgg) | (unsigned long long)count;
+    __syncthreads();   // list complete
+    if (kHasSH) {
       for (uint32_t j = tid; j < count; j += 256) {
         const int g = base + (int)list[j];
         float cr, cg, cb;
@@ -513,7 +527,41 @@ stripe_select_kernel(GcrPreprocessArgs a) {
                                      cr, cg, cb);
         a.records[g].q2 = make_float4(cr, cg, cb, 0.f);
       }
-      __syncthreads();   // list / wcount are rewritten by the next chunk
+    }
+    // global offset of the chunk: decoupled look-back (warp 0, 32 predecessors at a time)
+    if (warp == 0) {
+      unsigned long long excl = 0;
+      if (chunk != 0) {
+        long long t = (long long)chunk - 1;
+        while (true) {
+          const long long i = t - lane;
+          unsigned long long v;
+          do {
+            v = i >= 0 ? status[i] : kSelIncl;
+          } while (__any_sync(0xffffffffu, (v & ~kSelVal) == 0ull));
+          const unsigned incl = __ballot_sync(0xffffffffu, (v & ~kSelVal) == kSelIncl);
+          const int first = __ffs(incl) - 1;
+          unsigned long long c = (incl == 0u || lane <= first) ? (v & kSelVal) : 0ull;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+          excl += c;
+          if (incl != 0u) break;
+          t -= 32;
+        }
+        if (lane == 0) status[chunk] = kSelIncl | (excl + count);
+      }
+      if (lane == 0) {
+        s_excl = (uint32_t)excl;
+        if (chunk == nchunks - 1) *a.n_vis_out = (uint32_t)(excl + count);
+      }
+    }
+    __syncthreads();
+    const uint32_t excl = s_excl;
+    // the compacted, still index-ordered (key, index) list the depth sort works on
+    for (uint32_t j = tid; j < count; j += 256) {
+      const uint32_t g = (uint32_t)base + list[j];
+      a.depth_keys[excl + j] = a.depth_in[g];
+      a.sorted_init[excl + j] = g;
     }
   }
   const uint32_t wsum = __reduce_add_sync(0xffffffffu, my_tiles);

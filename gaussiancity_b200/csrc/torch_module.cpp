@@ -167,6 +167,89 @@ torch::Tensor mark_visible(const torch::Tensor& means3D, const torch::Tensor& vi
   return present;
 }
 
+// ---- adapter fusion: colors_precomp path through a pixel window; an undefined /
+// empty opacity or rotation tensor means opaque / identity (gcr_rasterizer_forward_window) --------
+std::tuple<int, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor>
+rasterize_gaussians_window(const torch::Tensor& background, const torch::Tensor& means3D,
+                           const torch::Tensor& colors, const torch::Tensor& opacity,
+                           const torch::Tensor& scales, const torch::Tensor& rotations,
+                           const float scale_modifier, const torch::Tensor& viewmatrix,
+                           const torch::Tensor& projmatrix, const float tan_fovx, const float tan_fovy,
+                           const int image_height, const int image_width, const int win_x, const int win_y,
+                           const int win_w, const int win_h, const bool debug) {
+  TORCH_CHECK(means3D.dim() == 2 && means3D.size(1) == 3, "means3D must have dimensions (num_points, 3)");
+  TORCH_CHECK(means3D.is_cuda(), "means3D must be a CUDA tensor (there is no CPU path)");
+  const torch::Device dev = means3D.device();
+  const c10::cuda::CUDAGuard guard(dev);
+  const int P = static_cast<int>(means3D.size(0));
+  const auto f32 = torch::TensorOptions().dtype(torch::kFloat32).device(dev);
+  const auto u8 = torch::TensorOptions().dtype(torch::kUInt8).device(dev);
+  torch::Tensor out_color = P != 0 ? torch::empty({kChannels, win_h, win_w}, f32)
+                                   : torch::zeros({kChannels, win_h, win_w}, f32);
+  torch::Tensor radii = torch::empty({P}, f32.dtype(torch::kInt32));
+  ByteBuffer geom{torch::empty({0}, u8), u8}, binning{torch::empty({0}, u8), u8}, img{torch::empty({0}, u8), u8};
+  int rendered = 0;
+  if (P != 0) {
+    const Arg bg = prep(background, "background", dev), m3 = prep(means3D, "means3D", dev);
+    const Arg col = prep(colors, "colors_precomp", dev), op = prep(opacity, "opacity", dev);
+    const Arg sc = prep(scales, "scales", dev), rot = prep(rotations, "rotations", dev, 16);
+    const Arg vm = prep(viewmatrix, "viewmatrix", dev), pm = prep(projmatrix, "projmatrix", dev);
+    rendered = gcr_rasterizer_forward_window(
+        alloc_bytes, &geom, alloc_bytes, &binning, alloc_bytes, &img, P, 0, 0, bg.ptr, image_width, image_height,
+        m3.ptr, nullptr, col.ptr, op.ptr, sc.ptr, scale_modifier, rot.ptr, nullptr, vm.ptr, pm.ptr, nullptr,
+        tan_fovx, tan_fovy, 0, out_color.data_ptr<float>(), radii.data_ptr<int>(), debug ? 1 : 0, win_x, win_y,
+        win_w, win_h, at::cuda::getCurrentCUDAStream(dev.index()).stream());
+    check(rendered, "rasterize_gaussians_window");
+  }
+  return std::make_tuple(rendered, out_color, radii, geom.t, binning.t, img.t);
+}
+
+// -> (dL_dmeans3D, dL_dcolors, dL_dscales, dL_dopacity | empty, dL_drotations | empty, dL_dmeans2D)
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor>
+rasterize_gaussians_backward_window(const torch::Tensor& background, const torch::Tensor& means3D,
+                                    const torch::Tensor& radii, const torch::Tensor& scales,
+                                    const torch::Tensor& rotations, const float scale_modifier,
+                                    const torch::Tensor& viewmatrix, const torch::Tensor& projmatrix,
+                                    const float tan_fovx, const float tan_fovy, const int image_height,
+                                    const int image_width, const int win_x, const int win_y, const int win_w,
+                                    const int win_h, const torch::Tensor& dL_dout_color,
+                                    const torch::Tensor& geomBuffer, const int R,
+                                    const torch::Tensor& binningBuffer, const torch::Tensor& imageBuffer,
+                                    const bool want_opacity, const bool debug) {
+  TORCH_CHECK(means3D.is_cuda(), "means3D must be a CUDA tensor (there is no CPU path)");
+  const torch::Device dev = means3D.device();
+  const c10::cuda::CUDAGuard guard(dev);
+  const int P = static_cast<int>(means3D.size(0));
+  const auto f32 = torch::TensorOptions().dtype(torch::kFloat32).device(dev);
+  auto make = [&](std::initializer_list<int64_t> shape) {
+    return P != 0 ? torch::empty(shape, f32) : torch::zeros(shape, f32);
+  };
+  const bool has_rot = rotations.numel() != 0;
+  torch::Tensor dL_dmeans3D = make({P, 3}), dL_dmeans2D = make({P, 3}), dL_dcolors = make({P, kChannels});
+  torch::Tensor dL_dcov3D = make({P, 6}), dL_dscales = make({P, 3});
+  torch::Tensor dL_dopacity = want_opacity ? make({P, 1}) : torch::empty({0}, f32);
+  torch::Tensor dL_drot = has_rot ? make({P, 4}) : torch::empty({0}, f32);
+  if (P != 0) {
+    const Arg bg = prep(background, "background", dev), m3 = prep(means3D, "means3D", dev);
+    const Arg sc = prep(scales, "scales", dev), rot = prep(rotations, "rotations", dev, 16);
+    const Arg vm = prep(viewmatrix, "viewmatrix", dev), pm = prep(projmatrix, "projmatrix", dev);
+    const Arg dpix = prep(dL_dout_color, "dL_dout_color", dev);
+    const torch::Tensor rad = radii.contiguous();
+    const int rc = gcr_rasterizer_backward_window(
+        P, 0, 0, R, bg.ptr, image_width, image_height, m3.ptr, nullptr, nullptr, sc.ptr, scale_modifier, rot.ptr,
+        nullptr, vm.ptr, pm.ptr, nullptr, tan_fovx, tan_fovy, rad.numel() ? rad.data_ptr<int>() : nullptr,
+        static_cast<char*>(geomBuffer.data_ptr()),
+        binningBuffer.numel() ? static_cast<char*>(binningBuffer.data_ptr()) : nullptr,
+        static_cast<char*>(imageBuffer.data_ptr()), dpix.ptr, dL_dmeans2D.data_ptr<float>(), nullptr,
+        want_opacity ? dL_dopacity.data_ptr<float>() : nullptr, dL_dcolors.data_ptr<float>(),
+        dL_dmeans3D.data_ptr<float>(), dL_dcov3D.data_ptr<float>(), nullptr, dL_dscales.data_ptr<float>(),
+        has_rot ? dL_drot.data_ptr<float>() : nullptr, debug ? 1 : 0, win_x, win_y, win_w, win_h,
+        at::cuda::getCurrentCUDAStream(dev.index()).stream());
+    check(rc, "rasterize_gaussians_backward_window");
+  }
+  return std::make_tuple(dL_dmeans3D, dL_dcolors, dL_dscales, dL_dopacity, dL_drot, dL_dmeans2D);
+}
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -174,5 +257,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("rasterize_gaussians", &rasterize_gaussians);
   m.def("rasterize_gaussians_backward", &rasterize_gaussians_backward);
   m.def("mark_visible", &mark_visible);
+  m.def("rasterize_gaussians_window", &rasterize_gaussians_window);
+  m.def("rasterize_gaussians_backward_window", &rasterize_gaussians_backward_window);
   m.def("abi_version", []() { return gcr_abi_version(); });
 }

@@ -87,7 +87,36 @@ def build(force=False, verbose=False):
     if verbose:
         print(" ".join(link))
     subprocess.check_call(link)
+    write_build_info(common)
     return out
+
+
+def build_info_path():
+    return os.path.join(OUT_DIR, "BUILD_INFO.json")
+
+
+def write_build_info(flags):
+    """The CUDA path reproduces the FMA contraction THIS nvcc chose for the reference sources
+    (DESIGN.md section 2); record the toolchain next to the .so so a parity failure on a pin built
+    by another compiler can be told from a regression."""
+    import json
+    try:
+        ver = subprocess.run(["nvcc", "--version"], capture_output=True, text=True).stdout.strip().splitlines()[-2:]
+    except Exception as e:  # pragma: no cover
+        ver = [repr(e)]
+    info = {"nvcc": ver, "arch": "sm_100a", "flags": flags, "deviation": "-include cstdint",
+            "sources": "extensions/diff_gaussian_rasterization (unmodified)"}
+    with open(build_info_path(), "w") as fh:
+        json.dump(info, fh, indent=1)
+
+
+def read_build_info():
+    import json
+    try:
+        with open(build_info_path()) as fh:
+            return json.load(fh)
+    except Exception:
+        return None
 
 
 # ---- BASELINE config 5 (models/generator.py G-step, ours vs REF): what the harness needs ---------

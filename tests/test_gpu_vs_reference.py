@@ -42,6 +42,13 @@ def ref(cuda_device):
     return m
 
 
+def _pin_toolchain():
+    """nvcc that built oracle/_ref (the bit-exact arithmetic is pinned to ITS contraction choices)."""
+    from oracle import build_ref
+    info = build_ref.read_build_info()
+    return f" [reference pin built with: {info['nvcc'] if info else 'unknown toolchain (no BUILD_INFO.json)'}]"
+
+
 def _relerr(a, b):
     den = b.double().norm().item()
     return (a.double() - b.double()).norm().item() / (den if den > 0 else 1.0)
@@ -57,8 +64,8 @@ def test_forward_backward_match_reference(ref, built_lib, cuda_device, name, P, 
     torch.cuda.synchronize()
 
     # ---- integer work: bit-exact ----
-    assert R == R_ref, f"num_rendered {R} != {R_ref}"
-    assert torch.equal(radii, radii_ref), f"radii differ at {(radii != radii_ref).sum().item()} of {P}"
+    assert R == R_ref, f"num_rendered {R} != {R_ref}" + _pin_toolchain()
+    assert torch.equal(radii, radii_ref), f"radii differ at {(radii != radii_ref).sum().item()} of {P}" + _pin_toolchain()
     gv = refext.ref_geom_views(geom_ref, P)
     ov = refext.our_views(P, R, W, H, geom, binning, img)
     vis = radii_ref > 0

@@ -14,6 +14,8 @@ Arms (VERDICT r1 task 6):
                 proof -- nothing of the caller changes.
   ours_wrapper  gaussiancity_b200.GaussianRasterizerWrapper(fast_camera=True) (Seam B + the
                 host-side camera path of SURVEY 8f-1) handed to the reference's helpers.
+  ours_fused    the same wrapper + gaussiancity_b200.adapter in place of the two helpers (SURVEY 8f-2:
+                structure-of-arrays attributes, no ones / identity tensors, crop inside the rasterizer).
 
 The reference's Python is imported from $GCR_REFERENCE_ROOT (default: baseline/_ref/GaussianCity,
 staged by oracle/build_ref.py; /root/reference where it exists).  Dependencies of files on the
@@ -75,7 +77,7 @@ class Cfg(dict):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--arm", choices=["reference", "ours", "ours_wrapper"], required=True)
+    ap.add_argument("--arm", choices=["reference", "ours", "ours_wrapper", "ours_fused"], required=True)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--points", type=int, default=16384)
@@ -127,8 +129,9 @@ def main():
     cam_pos_b, cam_quat_b = [np.asarray(cam_pos, dtype=np.float32)], [np.asarray(cam_quat, dtype=np.float32)]
 
     ours = None
-    if args.arm == "ours_wrapper":
+    if args.arm in ("ours_wrapper", "ours_fused"):
         import gaussiancity_b200 as ours
+        from gaussiancity_b200 import adapter
         gr = ours.GaussianRasterizerWrapper(CITY_K, CITY_SENSOR, device=dev, fast_camera=True)
     else:
         gr = dgr.GaussianRasterizerWrapper(K=CITY_K, sensor_size=CITY_SENSOR, flip_ud=False, device=dev)
@@ -137,7 +140,7 @@ def main():
     prof = {"fwd_host_ms": 0.0, "bwd_host_ms": 0.0, "calls": 0, "events": []}
     if args.profile:
         targets = [native_ext]
-        if args.arm == "ours_wrapper":
+        if args.arm in ("ours_wrapper", "ours_fused"):
             targets = [ours.dgr_ext]
         for mod in targets:
             for name, key in (("rasterize_gaussians", "fwd"), ("rasterize_gaussians_backward", "bwd")):
@@ -159,8 +162,11 @@ def main():
         torch.manual_seed(5000 + i)      # utils.helpers.get_z draws from the global generator
         z = utils.helpers.get_z(instances, cfg.Z_DIM)
         pt_attrs = G(proj_uv, rel_xyz, bch_idx, onehots, z, None, None)
-        gs_pts = utils.helpers.get_gaussian_points(abs_xyz.clone(), scales.clone(), pt_attrs)
-        fake = utils.helpers.get_gaussian_rasterization(gs_pts, gr, cam_pos_b, cam_quat_b, crp)
+        if args.arm == "ours_fused":   # no [B,N,14] tensor, crop folded into the rasterizer
+            fake = adapter.get_gaussian_rasterization_fused(abs_xyz, scales, pt_attrs, gr, cam_pos_b, cam_quat_b, crp)
+        else:
+            gs_pts = utils.helpers.get_gaussian_points(abs_xyz.clone(), scales.clone(), pt_attrs)
+            fake = utils.helpers.get_gaussian_rasterization(gs_pts, gr, cam_pos_b, cam_quat_b, crp)
         loss = l1(fake * msk, rgb * msk)
         G.zero_grad()
         loss.backward()

@@ -1,0 +1,37 @@
+"""One GPU playing rank `--rank` of `--world` of a balanced-striped frame (no peers needed: the
+forward never talks, the backward halves use a local accumulator): what each rank's kernels look
+like at N = world.  Run under ncu to capture project<*,deferred>, stripe_select, the small sorts,
+the blend kernels on one stripe and the chunked geometry backward."""
+import argparse, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+from gaussiancity_b200 import _cabi, ext
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--world", type=int, default=8)
+ap.add_argument("--rank", type=int, default=3)
+ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--workload", default="cfg4_5M_sh3_1080p")
+args = ap.parse_args()
+dev = torch.device("cuda:0")
+s = bench.make_scene(args.workload, dev)
+inp = bench.scene_inputs(s)
+P, H, W = s.means3D.shape[0], s.img_h, s.img_w
+G = torch.randn(3, H, W, device=dev)
+e = torch.Tensor([])
+out = None
+_cabi.profile_enable(True)
+for it in range(args.steps):
+    R, color, radii, geom, binning, img = ext.rasterize_gaussians(*bench.fwd_args(s, inp), shard_rank=args.rank,
+                                                                  shard_count=args.world, balanced=True)
+    acc = ext.rasterize_gaussians_backward_blend(inp["bg"], P, R, G, geom, binning, img, shard_rank=args.rank,
+                                                 shard_count=args.world)
+    out = ext.rasterize_gaussians_backward_geometry(inp["means3D"], radii, inp["scales"], inp["rotations"], 1.0, e,
+                                                    inp["view"], inp["proj"], s.tanfovx, s.tanfovy, H, W, inp["sh"],
+                                                    s.sh_degree, inp["campos"], geom, acc, shard_rank=args.rank,
+                                                    striped=True, out=out)
+torch.cuda.synchronize()
+st = _cabi.profile_read()
+print("rank", args.rank, "of", args.world, "R_local", R, "bounds", ext.stripe_bounds_of(geom, P, args.world).cpu().tolist())
+print("stages ms:", {k: round(v, 4) for k, v in st.items()}, "sum", round(sum(st.values()), 3))
