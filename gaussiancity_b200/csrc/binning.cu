@@ -162,15 +162,17 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-  for (int i = tid; i < kWarps * kBins; i += kThreads) (&warp_hist[0][0])[i] = 0;
   __syncthreads();
   const uint32_t tile = s_tile;
   const uint32_t n = load_count(n_ptr, n_max);
   if ((uint64_t)tile * kTile >= n) {
-    // surplus CTA (grid is sized for n_max).  An empty input still has to report its count.
+    // surplus CTA (the grid is sized for n_max; on a striped frame most CTAs of the later passes
+    // end here, so nothing is done before this test).  An empty input still has to report its count.
     if (n_out != nullptr && tile == 0 && tid == 0) *n_out = 0;
     return;
   }
+  for (int i = tid; i < kWarps * kBins; i += kThreads) (&warp_hist[0][0])[i] = 0;
+  __syncthreads();
 
   const uint32_t chunk_base = tile * (uint32_t)kTile;
   const uint32_t base = chunk_base + (uint32_t)warp * (32 * kItems);

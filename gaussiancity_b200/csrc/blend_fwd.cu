@@ -29,6 +29,7 @@ __global__ void __launch_bounds__(kBlendThreads)
 blend_fwd_kernel(GcrBlendArgs a) {
   __shared__ __align__(128) GcrRecord stage[kBlendStages][kBlendBatch];
   __shared__ __align__(8) uint64_t full_bar[kBlendStages];
+  __shared__ int vote[3];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile_x = a.tile_x0 + (int)blockIdx.x;
@@ -56,6 +57,7 @@ blend_fwd_kernel(GcrBlendArgs a) {
     gcr_mbar_init(&full_bar[0], kBlendThreads);
     gcr_mbar_init(&full_bar[1], kBlendThreads);
     gcr_mbar_fence_init();
+    vote[0] = vote[1] = vote[2] = 0;
   }
   __syncthreads();
 
@@ -124,9 +126,15 @@ blend_fwd_kernel(GcrBlendArgs a) {
         if (__ballot_sync(0xffffffffu, !done) == 0u) break;  // warp saturated
       }
     }
-    // CTA vote: everyone saturated -> leave; also fences this batch's smem reads before the
-    // stage is refilled two iterations later.
-    if (__syncthreads_count(done) == kBlendThreads) {
+    const bool warp_done_all = __ballot_sync(0xffffffffu, !done) == 0u;
+    // CTA vote: everyone saturated -> leave.  The barrier also fences this batch's shared-memory
+    // reads before the stage is refilled.  (A plain bar.sync plus a rotating flag rather than
+    // __syncthreads_count: same cost here, and compute-sanitizer's racecheck understands it.)
+    if (lane == 0 && !warp_done_all) vote[b % 3] = 1;
+    __syncthreads();
+    const bool any_active = vote[b % 3] != 0;
+    if (tid == 0) vote[(b + 2) % 3] = 0;   // used two iterations from now; ordered by the next barrier
+    if (!any_active) {
       ++b;
       break;
     }

@@ -345,7 +345,7 @@ __device__ void cut_stripes(volatile const uint32_t* h, int grid_y, int n, int* 
 }
 
 template <bool kHasSH, bool kDeferred>
-__global__ void __launch_bounds__(256, (kHasSH && !kDeferred) ? 3 : 4)
+__global__ void __launch_bounds__(256, (kHasSH && !kDeferred) ? 3 : 6)
 project_kernel(GcrPreprocessArgs a) {
   __shared__ uint32_t hist[kDeferred ? kPartRowsSmem : 1];
   __shared__ uint32_t s_sum;
@@ -624,7 +624,7 @@ inline unsigned persistent_grid(int n, int per_sm) {
 cudaError_t gcr_launch_project(const GcrPreprocessArgs& a, bool deferred, cudaStream_t stream) {
   if (a.P <= 0) return cudaSuccess;
   const bool sh = a.colors_precomp == nullptr;
-  const unsigned grid = deferred ? persistent_grid(a.P, 8) : (unsigned)((a.P + 255) / 256);
+  const unsigned grid = deferred ? persistent_grid(a.P, 6) : (unsigned)((a.P + 255) / 256);
   if (deferred) {
     if (sh) project_kernel<true, true><<<grid, 256, 0, stream>>>(a);
     else project_kernel<false, true><<<grid, 256, 0, stream>>>(a);

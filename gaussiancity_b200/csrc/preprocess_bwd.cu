@@ -383,11 +383,16 @@ template <bool kHasSH, int kItems>
 __global__ void __launch_bounds__(256)
 preprocess_bwd_kernel(GcrPreprocessBwdArgs a) {
   constexpr int kChunk = 256 * kItems;
-  __shared__ uint16_t list[kChunk];
+  // owned Gaussians (global indices) waiting to be differentiated: whatever does not fill a whole
+  // 256-thread batch is carried over to the next chunk, so every batch but a CTA's last runs with
+  // full warps (at N = 8 a 2048-Gaussian chunk holds ~270 owned ones: 256 + a 14-thread straggler
+  // batch otherwise)
+  __shared__ uint32_t queue[kChunk + 256];
   __shared__ uint32_t wcount[kItems][8];
   __shared__ int s_chunk;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nchunks = (a.range_count + kChunk - 1) / kChunk;
+  uint32_t pending = 0;   // block-uniform: entries in the queue
   while (true) {
     if (tid == 0) s_chunk = (int)atomicAdd(a.ticket, 1u);
     __syncthreads();
@@ -423,12 +428,24 @@ preprocess_bwd_kernel(GcrPreprocessBwdArgs a) {
         if (w < warp) before += c;
         count += c;
       }
-      if (owned[k]) list[before + __popc(bal[k] & ((1u << lane) - 1))] = (uint16_t)(k * 256 + tid);
+      if (owned[k]) queue[pending + before + __popc(bal[k] & ((1u << lane) - 1))] = (uint32_t)(base + k * 256 + tid);
     }
+    pending += count;
     __syncthreads();
-    for (uint32_t j = tid; j < count; j += 256) bwd_one<kHasSH>(a, base + (int)list[j], true);
-    __syncthreads();   // list / wcount / s_chunk are rewritten by the next chunk
+    uint32_t head = 0;
+    while (pending - head >= 256u) {
+      bwd_one<kHasSH>(a, (int)queue[head + tid], true);
+      head += 256;
+    }
+    const uint32_t rest = pending - head;   // < 256
+    uint32_t carry = 0;
+    if ((uint32_t)tid < rest) carry = queue[head + tid];
+    __syncthreads();
+    if ((uint32_t)tid < rest) queue[tid] = carry;
+    pending = rest;
+    // the next chunk's first barrier (ticket) orders these writes before anything reads the queue
   }
+  if ((uint32_t)tid < pending) bwd_one<kHasSH>(a, (int)queue[tid], true);
 }
 
 }  // namespace

@@ -21,8 +21,10 @@ P, H, W = s.means3D.shape[0], s.img_h, s.img_w
 G = torch.randn(3, H, W, device=dev)
 e = torch.Tensor([])
 out = None
-_cabi.profile_enable(True)
-for it in range(args.steps):
+for it in range(args.steps + 2):
+    if it == 2:   # two warm-up frames (module load, one-time function attributes), then profile
+        torch.cuda.synchronize()
+        _cabi.profile_enable(True)
     R, color, radii, geom, binning, img = ext.rasterize_gaussians(*bench.fwd_args(s, inp), shard_rank=args.rank,
                                                                   shard_count=args.world, balanced=True)
     acc = ext.rasterize_gaussians_backward_blend(inp["bg"], P, R, G, geom, binning, img, shard_rank=args.rank,
