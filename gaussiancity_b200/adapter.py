@@ -17,7 +17,7 @@ import torch
 
 from . import ext
 
-__all__ = ["render_gaussian_points", "get_gaussian_rasterization_fused"]
+__all__ = ["render_gaussian_points", "get_gaussian_rasterization_fused", "crop_to_window"]
 
 
 def _native():
@@ -70,6 +70,23 @@ class _WindowRasterize(torch.autograd.Function):
         return d_xyz, d_scales, d_rgb, d_opacity, d_rot, None, None
 
 
+def crop_to_window(W, H, crop, flip_lr, flip_ud):
+    """Pixel window (x, y, w, h) of the UNFLIPPED render that ends up as `crop` (dict x/y/w/h in the
+    coordinates of the wrapper's output, i.e. after its flips; None = everything) once the window is
+    flipped the way the wrapper flips the frame (DGR/__init__.py:421-424)."""
+    if crop is None:
+        x, y, w, h = 0, 0, int(W), int(H)
+    else:
+        x, y, w, h = int(crop["x"]), int(crop["y"]), int(crop["w"]), int(crop["h"])
+    if w <= 0 or h <= 0 or x < 0 or y < 0 or x + w > W or y + h > H:
+        raise ValueError(f"crop {crop} does not lie inside the {W}x{H} frame")
+    if flip_lr:
+        x = int(W) - (x + w)
+    if flip_ud:
+        y = int(H) - (y + h)
+    return x, y, w, h
+
+
 def render_gaussian_points(xyz, scales, rgb, wrapper, cam_position, cam_quaternion, opacity=None,
                            rotations=None, crop=None):
     """One frame: xyz/scales/rgb [N,3] (+ optional opacity [N,1], rotations [N,4]) through
@@ -77,16 +94,7 @@ def render_gaussian_points(xyz, scales, rgb, wrapper, cam_position, cam_quaterni
     crop = dict(x=, y=, w=, h=) in the coordinates of the wrapper's OUTPUT image (after its flips),
     exactly like the slice in utils/helpers.py:261-267; None = the full frame."""
     rs = wrapper._get_gaussian_rasterization_settings(cam_position, cam_quaternion)
-    W, H = int(rs.img_w), int(rs.img_h)
-    if crop is None:
-        x, y, w, h = 0, 0, W, H
-    else:
-        x, y, w, h = int(crop["x"]), int(crop["y"]), int(crop["w"]), int(crop["h"])
-    # the wrapper flips the rendered image (DGR/__init__.py:421-424): map the crop back through the flips
-    if wrapper.flip_lr:
-        x = W - (x + w)
-    if wrapper.flip_ud:
-        y = H - (y + h)
+    x, y, w, h = crop_to_window(rs.img_w, rs.img_h, crop, wrapper.flip_lr, wrapper.flip_ud)
     img = _WindowRasterize.apply(xyz, scales, rgb, opacity, rotations, rs, (x, y, w, h))
     if wrapper.flip_lr:
         img = torch.flip(img, dims=[2])

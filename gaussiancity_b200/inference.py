@@ -23,6 +23,7 @@ import numpy as np
 import torch
 
 from . import _cabi, ext
+from .adapter import crop_to_window
 
 __all__ = ["FrameRenderer"]
 
@@ -66,11 +67,7 @@ class FrameRenderer:
         w_ = self.wrapper
         rs = w_._get_gaussian_rasterization_settings(cam_position, cam_quaternion)
         W, H = int(rs.img_w), int(rs.img_h)
-        x, y, w, h = (0, 0, W, H) if crop is None else (int(crop["x"]), int(crop["y"]), int(crop["w"]), int(crop["h"]))
-        if w_.flip_lr:
-            x = W - (x + w)
-        if w_.flip_ud:
-            y = H - (y + h)
+        x, y, w, h = crop_to_window(W, H, crop, w_.flip_lr, w_.flip_ud)
         dev = self.device
         P = int(xyz.shape[0])
         lib = _cabi.lib()

@@ -200,3 +200,33 @@ def test_fast_camera_renders_the_same_image_as_the_reference_sequence():
         imgs.append(np.asarray(r.color, np.float64))
     den = np.linalg.norm(imgs[0])
     assert den > 0 and np.linalg.norm(imgs[0] - imgs[1]) / den <= 1e-4
+
+
+# ---- adapter fusion: crop of the flipped output frame -> window of the unflipped render ----
+
+def test_crop_to_window_commutes_with_the_wrapper_flips():
+    from gaussiancity_b200.adapter import crop_to_window
+    W, H = 960, 540
+    img = np.arange(W * H).reshape(H, W)
+    for flip_lr in (False, True):
+        for flip_ud in (False, True):
+            out = img[:, ::-1] if flip_lr else img
+            out = out[::-1, :] if flip_ud else out            # what the wrapper returns
+            for crop in (dict(x=160, y=46, w=640, h=448), dict(x=0, y=0, w=1, h=1), dict(x=959, y=539, w=1, h=1),
+                         dict(x=7, y=3, w=333, h=210), None):
+                x, y, w, h = crop_to_window(W, H, crop, flip_lr, flip_ud)
+                win = img[y:y + h, x:x + w]                   # what the rasterizer renders
+                win = win[:, ::-1] if flip_lr else win
+                win = win[::-1, :] if flip_ud else win
+                c = crop or dict(x=0, y=0, w=W, h=H)
+                assert np.array_equal(win, out[c["y"]:c["y"] + c["h"], c["x"]:c["x"] + c["w"]])
+    for bad in (dict(x=-1, y=0, w=10, h=10), dict(x=0, y=0, w=961, h=10), dict(x=0, y=100, w=10, h=441), dict(x=0, y=0, w=0, h=5)):
+        with pytest.raises(ValueError):
+            crop_to_window(W, H, bad, True, False)
+
+
+def test_package_reports_its_host_binding():
+    import gaussiancity_b200 as g
+    assert g.HOST_BINDING in ("native", "ctypes")
+    for n in ("rasterize_gaussians", "rasterize_gaussians_backward", "mark_visible"):
+        assert callable(getattr(g.dgr_ext, n))
