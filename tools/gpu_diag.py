@@ -43,7 +43,7 @@ for (P, W, H, deg, use_sh, seed) in [(1000,128,128,0,False,0), (100000,512,512,3
     report("conic.z", rec[vis][:, 4], gv["conic_opacity"][vis][:, 2])
     report("opacity", rec[vis][:, 5], gv["conic_opacity"][vis][:, 3])
     if use_sh:
-        report("rgb", rec[vis][:, 6:9], gv["rgb"][vis])
+        report("rgb", rec[vis][:, 8:11], gv["rgb"][vis])
     if R == R_ref and R > 0:
         bv = refext.ref_binning_views(bin_ref, R)
         report("point_list", ov["point_list"], bv["point_list"])
