@@ -195,9 +195,8 @@ def run_sharded_arm(args, s, inp, grad_out, rank, world, device, barrier):
     cam = eng._cam(s, inp)
     M = inp["sh"].shape[1] if inp["sh"].numel() else 0
     opts = dict(dtype=torch.float32, device=device)
-    out = (torch.empty((P, 3), **opts), torch.empty((P, 3), **opts), torch.empty((P, 1), **opts),
-           torch.empty((P, 3), **opts), torch.empty((P, 6), **opts), torch.empty((P, M, 3), **opts),
-           torch.empty((P, 3), **opts), torch.empty((P, 4), **opts))
+    # persistent gradient storage: packed 96-byte rows + dL_dsh (sharding.CudaBackend.backward_geometry)
+    out = (torch.empty((P, 24), **opts), torch.empty((P, M, 3), **opts))
 
     # ---- correctness gate (untimed): bit-identical frame, gradients <= 1e-4 --------------------
     check = {}

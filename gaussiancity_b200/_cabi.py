@@ -83,7 +83,7 @@ def _declare(l):
     l.gcr_rasterizer_backward_geometry.restype = c_int
     l.gcr_rasterizer_backward_geometry.argtypes = (
         [c_int] * 3 + [c_void_p] * 3 + [c_float] + [c_void_p] * 5 + [c_int, c_int, c_float, c_float] +
-        [c_void_p] * 12 + [c_int] * 6 + [c_void_p])
+        [c_void_p] * 12 + [c_int] * 6 + [c_void_p, c_void_p])
     l.gcr_stripe_partition.restype = c_int
     l.gcr_stripe_partition.argtypes = ([c_int, c_void_p, c_void_p, c_float] + [c_void_p] * 4 +
                                        [c_int, c_int, c_float, c_float, c_int] + [c_void_p] * 3)

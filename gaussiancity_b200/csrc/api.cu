@@ -580,7 +580,7 @@ int gcr_rasterizer_backward_geometry(int P, int D, int M, const float* means3D, 
                                      float* dL_dcov3D, float* dL_dsh, float* dL_dscale,
                                      float* dL_drot, int debug, int range_start, int range_count,
                                      int shard_rank, int striped, int clear_accumulator,
-                                     void* cuda_stream) {
+                                     float* dL_packed, void* cuda_stream) {
   (void)radii;  // ownership (which implies visibility) is recorded in the geometry buffer
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
   if (P <= 0) return 0;
@@ -593,8 +593,11 @@ int gcr_rasterizer_backward_geometry(int P, int D, int M, const float* means3D, 
   if (means3D == nullptr || viewmatrix == nullptr || projmatrix == nullptr || geom_buffer == nullptr ||
       accumulator == nullptr)
     return fail("means3D, viewmatrix, projmatrix, geom_buffer and accumulator must not be NULL");
-  if (dL_dmean2D == nullptr || dL_dcolor == nullptr || dL_dmean3D == nullptr || dL_dcov3D == nullptr)
+  if (dL_packed == nullptr &&
+      (dL_dmean2D == nullptr || dL_dcolor == nullptr || dL_dmean3D == nullptr || dL_dcov3D == nullptr))
     return fail("dL_dmean2D, dL_dcolor, dL_dmean3D and dL_dcov3D must not be NULL");
+  if (dL_packed != nullptr && (reinterpret_cast<uintptr_t>(dL_packed) & 31u) != 0)
+    return fail("dL_packed must be 32-byte aligned");
   if ((reinterpret_cast<uintptr_t>(accumulator) & 15u) != 0) return fail("accumulators must be 16-byte aligned");
   if (shs != nullptr && M > 16) return fail("at most 16 SH coefficients per Gaussian (degree 3) are supported");
   if (shs != nullptr && M > 0 && dL_dsh == nullptr) return fail("dL_dsh must not be NULL with SHs");
@@ -633,11 +636,12 @@ int gcr_rasterizer_backward_geometry(int P, int D, int M, const float* means3D, 
   a.dL_dcolor = dL_dcolor; a.dL_dmean3D = dL_dmean3D; a.dL_dcov3D = dL_dcov3D;
   a.dL_dsh = dL_dsh; a.dL_dscale = (scales != nullptr) ? dL_dscale : nullptr;
   a.dL_drot = (scales != nullptr && rotations != nullptr) ? dL_drot : nullptr;
+  a.packed_out = dL_packed;
   prof_mark(ST_GEOM_BWD, 0, stream);
   GCR_LAUNCH("preprocess_bwd", gcr_launch_preprocess_bwd(a, stream), debug, stream);
   prof_mark(ST_GEOM_BWD, 1, stream);
   // reference semantics: with a precomputed covariance the scale/rotation gradients are zeros
-  if (scales == nullptr && striped == 0) {
+  if (scales == nullptr && striped == 0 && dL_packed == nullptr) {
     if (dL_dscale)
       GCR_CUDA_OK(cudaMemsetAsync(dL_dscale + 3 * (size_t)range_start, 0,
                                   sizeof(float) * 3 * (size_t)range_count, stream));
@@ -670,7 +674,7 @@ int backward_impl(int P, int D, int M, int R, const float* background, int width
                                           height, tan_fovx, tan_fovy, radii, geom_buffer, grad_acc,
                                           dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor,
                                           dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, debug,
-                                          0, -1, 0, 0, 0, cuda_stream);
+                                          0, -1, 0, 0, 0, nullptr, cuda_stream);
 }
 }  // namespace
 

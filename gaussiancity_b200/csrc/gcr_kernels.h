@@ -179,6 +179,7 @@ struct GcrPreprocessBwdArgs {
   float* dL_dsh;       // [P,M,3] or null
   float* dL_dscale;    // [P,3] or null
   float* dL_drot;      // [P,4] or null
+  float* packed_out;   // [P,24] or null: all of the above except dL_dsh / dL_dconic in one 96-byte row
 };
 cudaError_t gcr_launch_preprocess_bwd(const GcrPreprocessBwdArgs& a, cudaStream_t stream);
 

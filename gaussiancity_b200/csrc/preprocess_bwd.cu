@@ -341,6 +341,24 @@ __forceinline__ __device__ void bwd_one(const GcrPreprocessBwdArgs& a, const int
     }
   }
 
+  if (a.packed_out != nullptr) {
+    // striped frames: a rank's Gaussians are scattered over the index range, so seven small rows
+    // per Gaussian would be seven partial-sector writes (each a read-modify-write in DRAM); one
+    // 96-byte row = three whole sectors.  Layout (floats): mean3D 0:3 | opacity 3 | scale 4:7 |
+    // mean2D 7:10 | colour 10:13 | cov3D 13:19 | pad 19 | rotation 20:24 (ext.py hands out views).
+    float4* o = reinterpret_cast<float4*>(a.packed_out + 24 * (size_t)idx);
+    o[0] = make_float4(dmean[0], dmean[1], dmean[2], o_op);
+    o[1] = make_float4(dscale[0], dscale[1], dscale[2], o_m2x);
+    o[2] = make_float4(o_m2y, 0.f, o_cr, o_cg);
+    o[3] = make_float4(o_cb, dcov[0], dcov[1], dcov[2]);
+    o[4] = make_float4(dcov[3], dcov[4], dcov[5], 0.f);
+    o[5] = make_float4(drot[0], drot[1], drot[2], drot[3]);
+    if (visible && a.clear_acc) {
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      a.grad_acc[idx].g0 = z; a.grad_acc[idx].g1 = z; a.grad_acc[idx].g2 = z;
+    }
+    return;
+  }
   a.dL_dmean2D[3 * idx + 0] = o_m2x;
   a.dL_dmean2D[3 * idx + 1] = o_m2y;
   a.dL_dmean2D[3 * idx + 2] = 0.f;

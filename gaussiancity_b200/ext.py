@@ -349,23 +349,38 @@ def rasterize_gaussians_backward_blend(background, P, R, dL_dout_color, geomBuff
     return grad_acc
 
 
+def packed_views(rows, dL_dsh):
+    """The 8-tuple of rasterize_gaussians_backward as views into a packed [P,24] gradient tensor
+    (layout: include/gcr_rasterizer.h, gcr_rasterizer_backward_geometry)."""
+    return (rows[:, 7:10], rows[:, 10:13], rows[:, 3:4], rows[:, 0:3], rows[:, 13:19], dL_dsh, rows[:, 4:7],
+            rows[:, 20:24])
+
+
 def rasterize_gaussians_backward_geometry(means3D, radii, scales, rotations, scale_modifier,
                                           cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy,
                                           image_height, image_width, sh, degree, campos, geomBuffer,
                                           grad_acc, range_start=0, range_count=-1, debug=False,
-                                          out=None, shard_rank=0, striped=False, clear_accumulator=False):
+                                          out=None, shard_rank=0, striped=False, clear_accumulator=False,
+                                          packed=None):
     """Second half of the backward: per-Gaussian geometry gradients, for the Gaussians within
     [range_start, range_start+range_count) that `shard_rank` owns, from the (reduced) accumulator
     (a [P,12] tensor or a device address).  Returns the same 8-tuple as
     rasterize_gaussians_backward.  striped=False: the rows of all other Gaussians in the range are
     written as zeros; striped=True: they are left untouched (uninitialised unless `out` is
-    supplied)."""
+    supplied).  packed=(rows [P,24], dL_dsh [P,M,3]) (or True to allocate them): the kernel writes one
+    96-byte row per Gaussian and the returned tensors are views into it (see packed_views)."""
     lib = _cabi.lib()
     device = means3D.device
     P = int(means3D.size(0))
     M = int(sh.size(1)) if sh.numel() != 0 else 0
     opts = dict(dtype=torch.float32, device=device)
     with torch.cuda.device(device):
+        rows = None
+        if packed is not None and packed is not False:
+            if packed is True:
+                packed = (torch.empty((P, 24), **opts), torch.empty((P, M, 3), **opts))
+            rows, dsh_p = packed
+            out = packed_views(rows, dsh_p)
         if out is None:
             out = (torch.empty((P, 3), **opts), torch.empty((P, 3), **opts), torch.empty((P, 1), **opts),
                    torch.empty((P, 3), **opts), torch.empty((P, 6), **opts), torch.empty((P, M, 3), **opts),
@@ -386,9 +401,12 @@ def rasterize_gaussians_backward_geometry(means3D, radii, scales, rotations, sca
                 _ptr(rotations), _ptr(cov3D_precomp), _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos),
                 int(image_width), int(image_height), float(tan_fovx), float(tan_fovy),
                 _ptr(radii.contiguous()), ctypes.c_void_p(geomBuffer.data_ptr()), acc_ptr,
-                _ptr(dL_dmeans2D), None, _ptr(dL_dopacity), _ptr(dL_dcolors), _ptr(dL_dmeans3D),
-                _ptr(dL_dcov3D), _ptr(dL_dsh), _ptr(dL_dscales), _ptr(dL_drot), int(bool(debug)),
+                None if rows is not None else _ptr(dL_dmeans2D), None,
+                None if rows is not None else _ptr(dL_dopacity), None if rows is not None else _ptr(dL_dcolors),
+                None if rows is not None else _ptr(dL_dmeans3D), None if rows is not None else _ptr(dL_dcov3D),
+                _ptr(dL_dsh), None if rows is not None else _ptr(dL_dscales),
+                None if rows is not None else _ptr(dL_drot), int(bool(debug)),
                 int(range_start), int(range_count), int(shard_rank), int(bool(striped)),
-                int(bool(clear_accumulator)), _stream_ptr(device))
+                int(bool(clear_accumulator)), _ptr(rows) if rows is not None else None, _stream_ptr(device))
             _cabi.check(rc, "rasterize_gaussians_backward_geometry")
     return out

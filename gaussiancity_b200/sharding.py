@@ -107,13 +107,20 @@ class CudaBackend:
             shard_rank=rank, shard_count=world)
 
     def backward_geometry(self, state, inp, cam, grad_acc, rank, world, out=None, clear=False):
+        """out: None, a tuple of 8 dense tensors, or -- striped frames -- `(rows [P,24], dL_dsh)`: the
+        packed form (one 96-byte row per owned Gaussian instead of seven scattered partial-sector
+        writes); the returned gradients are then views into `rows`."""
         from . import ext
         e = torch.Tensor([])
+        packed = None
+        if world > 1:
+            packed = out if (out is not None and len(out) == 2) else True
+            out = None
         return ext.rasterize_gaussians_backward_geometry(
             inp["means3D"], state["radii"], inp["scales"], inp["rotations"], 1.0, e, cam["view"],
             cam["proj"], cam["tanfovx"], cam["tanfovy"], cam["img_h"], cam["img_w"],
             inp.get("sh", e), cam["sh_degree"], cam["campos"], state["geom"], grad_acc,
-            shard_rank=rank, striped=world > 1, clear_accumulator=clear, out=out)
+            shard_rank=rank, striped=world > 1, clear_accumulator=clear, out=out, packed=packed)
 
     def owner_mask(self, state, inp, rank):
         from . import ext

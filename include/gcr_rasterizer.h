@@ -165,7 +165,11 @@ GCR_API int gcr_rasterizer_backward(int P, int D, int M, int R, const float* bac
  * _geometry turns accumulator rows into the public gradients for the Gaussians this rank owns
  * within [range_start, range_start + range_count) (range_count < 0: all).  striped == 0: rows of
  * the other Gaussians are written as zeros (reference semantics); striped != 0: they are left
- * untouched (their owners write them). */
+ * untouched (their owners write them).  dL_packed (optional, [P,24] fp32, 32-byte aligned): when
+ * given, everything except dL_dsh / dL_dconic goes into ONE 96-byte row per Gaussian instead of the
+ * seven separate arrays (floats: mean3D 0:3 | opacity 3 | scale 4:7 | mean2D 7:10 | colour 10:13 |
+ * cov3D 13:19 | pad | rotation 20:24) -- on striped frames a rank's Gaussians are scattered over
+ * the index range, and one row of whole 32-byte sectors replaces seven partial-sector writes. */
 GCR_API int gcr_rasterizer_backward_blend(int P, int R, const float* background, int width, int height,
                                   char* geom_buffer, char* binning_buffer, char* image_buffer,
                                   const float* dL_dpix, float* const* accumulators,
@@ -183,7 +187,7 @@ GCR_API int gcr_rasterizer_backward_geometry(int P, int D, int M, const float* m
                                      float* dL_dcov3D, float* dL_dsh, float* dL_dscale,
                                      float* dL_drot, int debug, int range_start, int range_count,
                                      int shard_rank, int striped, int clear_accumulator,
-                                     void* cuda_stream);
+                                     float* dL_packed, void* cuda_stream);
 
 /* present: P bytes (bool). Returns 0 or < 0. */
 GCR_API int gcr_rasterizer_mark_visible(int P, const float* means3D, const float* viewmatrix,

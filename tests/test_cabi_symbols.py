@@ -107,19 +107,20 @@ def test_argument_validation_returns_errors_without_touching_the_device(built_li
     def geometry(**kw):
         a = dict(P=4, D=0, M=1, means=good, shs=good, scales=good, rot=good, cov=None, view=good, proj=good,
                  campos=good, W=16, H=16, geom=good, acc=good, m2d=good, dsh=good, drot=good, start=0, count=-1,
-                 rank=0)
+                 rank=0, packed=None)
         a.update(kw)
         return l.gcr_rasterizer_backward_geometry(
             a["P"], a["D"], a["M"], a["means"], a["shs"], a["scales"], 1.0, a["rot"], a["cov"], a["view"],
             a["proj"], a["campos"], a["W"], a["H"], 1.0, 1.0, None, a["geom"], a["acc"], a["m2d"], None, good,
-            good, good, good, a["dsh"], good, a["drot"], 0, a["start"], a["count"], a["rank"], 0, 0, None)
+            good, good, good, a["dsh"], good, a["drot"], 0, a["start"], a["count"], a["rank"], 0, 0, a["packed"], None)
 
     assert geometry(P=0) == 0
     for kw, msg in [(dict(acc=None), "must not be NULL"), (dict(acc=C.c_void_p(0x10008)), "16-byte aligned"),
                     (dict(geom=None), "must not be NULL"), (dict(m2d=None), "must not be NULL"),
                     (dict(dsh=None), "dL_dsh"), (dict(M=25), "at most 16 SH"), (dict(start=3, count=2), "out of bounds"),
                     (dict(scales=None), "scale/rotation"), (dict(drot=C.c_void_p(0x10004)), "dL_drot"),
-                    (dict(W=0), "image size"), (dict(rank=16), "shard")]:
+                    (dict(W=0), "image size"), (dict(rank=16), "shard"),
+                    (dict(packed=C.c_void_p(0x10010)), "32-byte aligned")]:
         assert geometry(**kw) < 0, kw
         assert msg in _cabi.last_error(), (kw, _cabi.last_error())
 

@@ -254,6 +254,15 @@ def test_tile_row_stripes_partition_the_frame(big, balanced):
             out=out, shard_rank=k, striped=True)
     for a, b in zip(out, grads):
         assert (a.double() - b.double()).norm().item() <= 1e-5 * max(b.double().norm().item(), 1e-30)
+    # packed form (one 96-byte row per owned Gaussian): views into the rows equal the dense outputs
+    gk, rk = states[1]
+    own1 = ours.owner_bytes(gk, P) == 1
+    pv = ours.rasterize_gaussians_backward_geometry(
+        s.means3D, rk, s.scales, s.rotations, 1.0, e, s.view_matrix, s.proj_matrix, s.tanfovx, s.tanfovy,
+        s.img_h, s.img_w, s.shs, s.sh_degree, s.campos, gk, acc.float(), shard_rank=1, striped=True, packed=True)
+    for a, b in zip(pv, out):
+        assert a.shape == b.shape
+        assert torch.equal(a[own1], b[own1])
     # and the per-slice form on one stripe (range_start / range_count) still reproduces it
     out = None
     third = (P + 2) // 3
