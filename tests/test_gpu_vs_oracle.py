@@ -261,8 +261,8 @@ def test_tile_row_stripes_partition_the_frame(big, balanced):
         s.means3D, rk, s.scales, s.rotations, 1.0, e, s.view_matrix, s.proj_matrix, s.tanfovx, s.tanfovy,
         s.img_h, s.img_w, s.shs, s.sh_degree, s.campos, gk, acc.float(), shard_rank=1, striped=True, packed=True)
     for a, b in zip(pv, out):
-        assert a.shape == b.shape
-        assert torch.equal(a[own1], b[own1])
+        assert a.shape == b.shape      # (the two output branches of the kernel may contract differently: last-bit noise)
+        assert (a[own1].double() - b[own1].double()).norm().item() <= 1e-6 * max(b[own1].double().norm().item(), 1e-30)
     # and the per-slice form on one stripe (range_start / range_count) still reproduces it
     out = None
     third = (P + 2) // 3
