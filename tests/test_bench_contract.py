@@ -29,7 +29,7 @@ def test_default_workload_is_the_headline_config():
 
 
 def test_traffic_file_matches_default_workload():
-    d = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+    d = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
     sys.path.insert(0, ROOT)
     import bench
     assert d["workload"] == bench.DEFAULT_WORKLOAD
