@@ -305,12 +305,13 @@ def run_sharded_arm(args, s, inp, grad_out, rank, world, device, barrier):
     mode = ("Gaussians resident on every rank" if args.shard_mode == "replicated" else
             "rank 0 NCCL-broadcasts all Gaussian buffers every frame (prefetched one frame ahead)")
     exch = ("per-Gaussian gradient sums added straight into the owner rank's accumulator over NVLink peer "
-            "memory inside the blend kernel + one cross-GPU barrier kernel" if args.exchange == "peer" else
-            "partial [P,12] accumulators all_reduced by NCCL")
+            "memory inside the blend kernel + one cross-GPU barrier kernel" if eng.exchange == "peer" else
+            "partial [P,12] accumulators all_reduced by NCCL" +
+            (f" (peer mapping unavailable: {eng.peer_error})" if args.exchange == "peer" else ""))
     extra = {"parallelism": f"tile-row stripes x{world} ({'equal-height' if args.equal_stripes else 'balanced by per-row instance counts'}), "
                             f"{mode}; {exch}; frame {'assembled on every rank (all_reduce)' if args.assemble else 'left in stripes'}; "
                             f"gradients left with their owners",
-             "shard_mode": args.shard_mode, "exchange": args.exchange, "assemble": bool(args.assemble),
+             "shard_mode": args.shard_mode, "exchange": eng.exchange, "assemble": bool(args.assemble),
              "ms_other_assembly_mode": ms_alt, "num_rendered_local_max": int(rmax.item()),
              "stripe_bounds": bounds_h if not args.no_e2e else None, "check": check}
     return dict(ms=ms, ms_fwd=ms_fwd, R=R_total, V=None, stages=stages, P=P, W=W, H=H, s=s, inp=inp,
@@ -553,7 +554,8 @@ def main():
                                     "sample": "full workload on the GPU: the reference has no CPU "
                                               "implementation of this path (SURVEY.md 8c)"}
         else:
-            line["gpu_launches"] = kernels_per_step(W, H) * args.steps   # per rank
+            # per rank; a striped frame adds the stripe-select kernel and the cross-GPU barrier kernel
+            line["gpu_launches"] = (kernels_per_step(W, H) + (2 if world_eff > 1 else 0)) * args.steps
             line["parallelism"] = res["extra"].pop("parallelism", "single GPU")
             if res["extra"]:
                 line["sharding"] = res["extra"]

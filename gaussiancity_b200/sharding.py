@@ -214,7 +214,8 @@ class TileShardedRasterizer:
         self.balanced = balanced
         self.remote_scalar = remote_scalar
         self.last_num_rendered_local = None
-        self._grad_out = None
+        self._peer_checked = False
+        self.peer_error = None
 
     # -- collectives -------------------------------------------------------------------------
     def broadcast_gaussians(self, inp, src=0):
@@ -262,6 +263,20 @@ class TileShardedRasterizer:
         """-> (grads, owner_mask): dense [P,...] gradient tensors in which this rank has written
         the rows of the Gaussians it owns (all visible ones when world == 1, where the remaining
         rows are zeros as in the reference)."""
+        if self.exchange == "peer" and not self._peer_checked:
+            # every rank must take the same path: agree once on whether peer mapping works everywhere
+            ok = 1
+            try:
+                self.backend.peer_setup(inp["means3D"].shape[0], self.rank, self.world, self.group)
+            except Exception as e:   # no P2P / IPC on this box: fall back to the collective formulation
+                ok, self.peer_error = 0, repr(e)
+            flag = torch.tensor([ok], device=inp["means3D"].device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            if int(flag.item()) == 0:
+                if ok:
+                    self.backend.peer_teardown()
+                self.exchange = "collective"
+            self._peer_checked = True
         if self.exchange == "peer":
             self.backend.peer_setup(inp["means3D"].shape[0], self.rank, self.world, self.group)
             grads = self.backend.peer_backward(state, inp, cam, grad_out, self.rank, self.world, out=out,
