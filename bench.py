@@ -476,7 +476,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=sorted(WORKLOADS), default=DEFAULT_WORKLOAD)
+    ap.add_argument("--workload", choices=sorted(WORKLOADS) + ["grid_encoder"], default=DEFAULT_WORKLOAD)
     ap.add_argument("--shard-mode", choices=["broadcast", "replicated"], default="replicated",
                     help="N>1: 'replicated' (default; consistent with `value` = inputs resident in HBM) = "
                          "every rank holds the Gaussians; 'broadcast' = rank 0 owns them and NCCL-broadcasts all "
@@ -492,6 +492,14 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.workload == "grid_encoder":
+        # the generator's hash-grid positional encoder, ours vs the reference extension
+        # (one GPU; bench_grid_encoder.py holds the leg and documents the line it prints)
+        if int(os.environ.get("RANK", "0")) == 0:
+            import bench_grid_encoder
+            bench_grid_encoder.main(["--impl", args.impl, "--steps", str(args.steps), "--warmup", str(args.warmup)] +
+                                    (["--no-cpu-baseline"] if args.no_cpu_baseline else []))
+        return
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

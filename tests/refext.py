@@ -121,3 +121,52 @@ def scene_backward_args(s, radii, grad_out, geom, R, binning, img, scale_modifie
             s.scales, s.rotations, scale_modifier, e, s.view_matrix, s.proj_matrix, s.tanfovx, s.tanfovy,
             grad_out, s.shs if s.shs is not None else e, s.sh_degree, s.campos, geom, R, binning,
             img, False)
+
+
+# ---- grid encoder ---------------------------------------------------------------------
+def _load_extension_file(name, path):
+    """Load a pybind .so by path without registering it in sys.modules (two modules called
+    `grid_encoder_ext` -- the reference's and ours -- live in one process)."""
+    import importlib.machinery
+    import importlib.util
+    loader = importlib.machinery.ExtensionFileLoader(name, path)
+    spec = importlib.util.spec_from_file_location(name, path, loader=loader)
+    mod = importlib.util.module_from_spec(spec)
+    loader.exec_module(mod)
+    return mod
+
+
+def load_reference_grid_ext():
+    """The UNMODIFIED reference grid_encoder_ext built by oracle/build_ref.build_grid_encoder(), or None."""
+    hits = glob.glob(os.path.join(REF_DIR, "grid_encoder_ext*.so"))
+    return _load_extension_file("grid_encoder_ext", hits[0]) if hits else None
+
+
+def load_our_grid_ext():
+    from gaussiancity_b200 import build
+    return _load_extension_file("grid_encoder_ext", build.native_module_path("grid_encoder_ext"))
+
+
+def load_reference_grid_python(ext_module, alias):
+    """The reference's own extensions/grid_encoder/__init__.py (staged under baseline/_ref by
+    oracle/build_ref.py, or /root/reference where it exists), executed with `import grid_encoder_ext`
+    resolving to `ext_module`.  Returns the module (GridEncoder, GridEncoderFunction) or None."""
+    import importlib.util
+    for root in (os.path.join(ROOT, "baseline", "_ref", "GaussianCity"), "/root/reference"):
+        path = os.path.join(root, "extensions", "grid_encoder", "__init__.py")
+        if os.path.exists(path):
+            break
+    else:
+        return None
+    saved = sys.modules.get("grid_encoder_ext")
+    sys.modules["grid_encoder_ext"] = ext_module
+    try:
+        spec = importlib.util.spec_from_file_location(alias, path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        if saved is None:
+            sys.modules.pop("grid_encoder_ext", None)
+        else:
+            sys.modules["grid_encoder_ext"] = saved
+    return mod

@@ -1,0 +1,214 @@
+"""CPU: the hash-grid encoder's oracle, host logic and C ABI -- no GPU.
+
+* oracle/grid_oracle.c against the golden vectors the UNMODIFIED reference extension produced on a
+  B200 (tests/golden/grid/*.npz, tests/golden/make_golden_grid.py);
+* the same oracle against an independent vectorised fp64 PyTorch restatement and its autograd
+  (gradient ground truth for the embedding and the input gradients);
+* GridEncoder's constructor logic (level table sizes) against the values the reference recorded;
+* libgcr_grid_encoder.so loads and exports every symbol include/gcr_grid_encoder.h declares,
+  refuses bad arguments before touching a device, and a missing library fails loudly.
+"""
+import ctypes
+import glob
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import grid_oracle as go
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "grid", "*.npz")))
+HEADER = os.path.join(ROOT, "include", "gcr_grid_encoder.h")
+
+
+def rel(a, b):
+    den = np.linalg.norm(b)
+    return float(np.linalg.norm(np.asarray(a, np.float64) - np.asarray(b, np.float64)) / (den if den > 0 else 1.0))
+
+
+def random_case(D, C, L, H, desired, log2T, gridtype, align, B, seed, oob=2):
+    g = np.random.default_rng(seed)
+    offsets = go.level_offsets(D, L, H, 2, log2T, align)
+    emb = g.uniform(-1, 1, (int(offsets[-1]), C)).astype(np.float32)
+    x = g.uniform(0, 1, (B, D)).astype(np.float32)
+    x[0], x[1] = 0.0, 1.0
+    for i in range(oob):
+        x[2 + i, i % D] = -0.1 if i % 2 == 0 else 1.2
+    pls = 2 ** (math.log2(desired / H) / (L - 1))
+    return dict(inputs=x, embeddings=emb, offsets=offsets, per_level_scale=pls, base_resolution=H,
+                gridtype=gridtype, align_corners=align)
+
+
+CASES = [
+    dict(D=5, C=8, L=4, H=16, desired=2048, log2T=12, gridtype=0, align=False, B=40, seed=1),
+    dict(D=3, C=2, L=6, H=4, desired=128, log2T=10, gridtype=0, align=False, B=50, seed=2),
+    dict(D=2, C=4, L=5, H=8, desired=256, log2T=9, gridtype=1, align=True, B=30, seed=3),
+    dict(D=4, C=1, L=3, H=16, desired=100, log2T=11, gridtype=0, align=False, B=20, seed=4),
+    dict(D=3, C=4, L=4, H=8, desired=64, log2T=8, gridtype=1, align=False, B=30, seed=5),   # tiled + wrapped
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"D{c['D']}C{c['C']}g{c['gridtype']}a{int(c['align'])}")
+def test_oracle_matches_independent_fp64_restatement_and_autograd(case):
+    c = random_case(**case)
+    B, D = c["inputs"].shape
+    C = c["embeddings"].shape[1]
+    L = len(c["offsets"]) - 1
+    out, dy_dx = go.forward(c["inputs"], c["embeddings"], c["offsets"], c["per_level_scale"], c["base_resolution"],
+                            True, c["gridtype"], c["align_corners"])
+    x = torch.tensor(c["inputs"], dtype=torch.float64, requires_grad=True)
+    e = torch.tensor(c["embeddings"], dtype=torch.float64, requires_grad=True)
+    y = go.torch_encode(x, e, c["offsets"], c["per_level_scale"], c["base_resolution"], c["gridtype"],
+                        c["align_corners"])
+    want = y.detach().numpy().reshape(B, L, C).transpose(1, 0, 2)
+    assert rel(out, want) < 2e-6
+    # out-of-range points encode to zeros
+    oob = ((c["inputs"] < 0) | (c["inputs"] > 1)).any(axis=1)
+    assert oob.sum() >= 2 and not out[:, oob].any() and not dy_dx[oob].any()
+    g = np.random.default_rng(77).standard_normal((L, B, C)).astype(np.float32)
+    (y * torch.tensor(g.transpose(1, 0, 2).reshape(B, L * C), dtype=torch.float64)).sum().backward()
+    ge, gi = go.backward(g, c["inputs"], c["embeddings"].shape[0], c["offsets"], c["per_level_scale"],
+                         c["base_resolution"], dy_dx, c["gridtype"], c["align_corners"])
+    assert rel(ge, e.grad.numpy()) < 2e-6
+    assert rel(gi, x.grad.numpy()) < 2e-5
+
+
+def test_oracle_corner_rows_hash_and_dense():
+    """Integer work, checked by hand-rolled numpy: level 0 of a D=2 grid with a table large enough is
+    dense (row = x + y * (res + 1)); a D=3 level that does not fit is the prime XOR hash."""
+    x = np.array([[0.3, 0.7], [0.0, 1.0]], np.float32)
+    offsets = np.array([0, 512], np.int32)           # (16+1)^2 = 289 <= 512 -> dense
+    rows, w = go.corner_rows(x, offsets, 2.0, 16)
+    scale = np.float32(15.0)
+    pos = x * scale + np.float32(0.5)
+    cell = np.floor(pos).astype(np.uint32)
+    for b in range(2):
+        for corner in range(4):
+            cx, cy = cell[b, 0] + (corner & 1), cell[b, 1] + (corner >> 1)
+            assert rows[0, b, corner] == (cx + cy * 17) % 512
+    assert np.allclose(w.sum(axis=2), 1.0, atol=1e-6)
+    x3 = np.array([[0.21, 0.55, 0.93]], np.float32)
+    offsets = np.array([0, 1024], np.int32)          # 17^3 = 4913 > 1024 -> hashed
+    rows, _ = go.corner_rows(x3, offsets, 2.0, 16)
+    cell = np.floor(x3 * scale + np.float32(0.5)).astype(np.uint64)
+    primes = (1, 2654435761, 805459861)
+    for corner in range(8):
+        h = 0
+        for d in range(3):
+            h ^= (int(cell[0, d]) + ((corner >> d) & 1)) * primes[d] & 0xFFFFFFFF
+        assert rows[0, 0, corner] == h % 1024
+    # tiled grid type never hashes: the partial dense index wraps instead
+    rows_t, _ = go.corner_rows(x3, offsets, 2.0, 16, gridtype=1)
+    for corner in range(8):
+        idx = sum((int(cell[0, d]) + ((corner >> d) & 1)) * 17 ** d for d in range(3))
+        assert rows_t[0, 0, corner] == idx % 1024
+
+
+@pytest.mark.skipif(not GOLDEN, reason="golden vectors not generated yet (tests/golden/make_golden_grid.py)")
+@pytest.mark.parametrize("path", GOLDEN, ids=lambda p: os.path.basename(p)[:-4])
+def test_oracle_reproduces_reference_golden_vectors(path):
+    """Outputs of the unmodified reference extension (B200).  Floats to 2e-6 norm-relative: the one
+    operation the CPU cannot reproduce bit for bit is the GPU's exp2f (MUFU.EX2) in the level scale;
+    with per_level_scale = 2 it is exact and so is the whole forward."""
+    z = np.load(path)
+    pls, H = float(z["per_level_scale"]), int(z["base_resolution"])
+    gt, al = int(z["gridtype"]), bool(z["align_corners"])
+    out, dy_dx = go.forward(z["inputs"], z["embeddings"], z["offsets"], pls, H, True, gt, al)
+    exact = abs(pls - 2.0) < 1e-12
+    if exact:
+        assert np.array_equal(out, z["outputs"])
+        assert np.array_equal(dy_dx, z["dy_dx"])
+    else:
+        assert rel(out, z["outputs"]) < 2e-6
+        assert rel(dy_dx, z["dy_dx"]) < 2e-5
+    ge, gi = go.backward(z["grad"], z["inputs"], z["embeddings"].shape[0], z["offsets"], pls, H, z["dy_dx"], gt, al)
+    assert rel(ge, z["grad_embeddings"]) < 2e-6
+    assert np.array_equal(gi, z["grad_inputs"]) or rel(gi, z["grad_inputs"]) < 1e-6
+    # module surface: inputs in [-1, 1], output [B, L*C]
+    L, B, C = z["outputs"].shape
+    assert np.array_equal(z["module_outputs"], z["outputs"].transpose(1, 0, 2).reshape(B, L * C))
+    # host logic: the level table sizes GridEncoder.__init__ derived
+    D = z["inputs"].shape[1]
+    assert np.array_equal(go.level_offsets(D, L, H, 2, int(z["log2_hashmap_size"]), al), z["offsets"])
+
+
+def test_grid_encoder_module_host_logic():
+    """Constructor attributes, parameter / buffer names and shapes as the reference
+    (extensions/grid_encoder/__init__.py:127-165); no device work."""
+    from gaussiancity_b200.grid_encoder import GridEncoder, level_offsets
+    enc = GridEncoder(in_channels=5, n_levels=16, lvl_channels=8, desired_resolution=2048)
+    assert enc.output_dim == 128 and enc.gridtype_id == 0 and enc.max_params == 2 ** 19
+    assert abs(enc.per_level_scale - 2 ** (7 / 15)) < 1e-12
+    assert enc.offsets.dtype == torch.int32 and enc.offsets.shape == (17,)
+    assert int(enc.offsets[-1]) == 16 * 2 ** 19          # (16+1)^5 > 2^19: every level is a full hash table
+    assert enc.embeddings.shape == (16 * 2 ** 19, 8) and enc.embeddings.dtype == torch.float32
+    assert float(enc.embeddings.abs().max()) <= 1e-4
+    assert set(dict(enc.named_parameters())) == {"embeddings"} and set(dict(enc.named_buffers())) == {"offsets"}
+    assert np.array_equal(level_offsets(5, 16), go.level_offsets(5, 16))
+    small = level_offsets(2, 4, 16, 2, 19)
+    assert list(small) == [0, 296, 1392, 5624, 22272]      # ceil((res+1)^2 / 8) * 8 per level, dense
+    tiled = GridEncoder(3, 4, 2, 128, gridtype="tiled", align_corners=True, log2_hashmap_size=10)
+    assert tiled.gridtype_id == 1 and tiled.align_corners
+
+
+def test_cpu_tensors_are_refused():
+    from gaussiancity_b200.grid_encoder import GridEncoder
+    enc = GridEncoder(3, 2, 2, 32, log2_hashmap_size=8)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        enc(torch.rand(4, 3) * 2 - 1)
+
+
+def declared_symbols():
+    src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    return sorted(set(re.findall(r"GCR_GRID_API\s+[\w\s\*]+?\b(gcr_grid_\w+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def grid_lib():
+    from gaussiancity_b200 import build
+    return build.build_grid_library()
+
+
+def test_library_exports_every_declared_symbol(grid_lib):
+    from gaussiancity_b200 import grid_encoder as ge
+    lib = ctypes.CDLL(grid_lib)
+    syms = declared_symbols()
+    assert "gcr_grid_encode_forward" in syms and "gcr_grid_encode_backward" in syms
+    assert not [s for s in syms if not hasattr(lib, s)]
+    assert sorted(ge.EXPORTED_SYMBOLS) == syms
+    assert ge.lib().gcr_grid_abi_version() == ge.ABI_VERSION
+
+
+def test_argument_validation_without_a_device(grid_lib):
+    from gaussiancity_b200 import grid_encoder as ge
+    l = ge.lib()
+    p = ctypes.c_void_p(0x10000)     # never dereferenced on the host
+
+    def fwd(B=4, D=3, C=2, L=2, inputs=p, emb=p, out=p, dy=p, calc=0):
+        return l.gcr_grid_encode_forward(inputs, emb, p, out, B, D, C, L, 1.0, 16, calc, dy, 0, 0, None)
+
+    def err():
+        return l.gcr_grid_last_error().decode()
+
+    assert fwd(B=0) == 0                                   # nothing to do
+    assert fwd(inputs=None) != 0 and "NULL" in err()
+    assert fwd(emb=None) != 0 and "NULL" in err()
+    assert fwd(calc=1, dy=None) != 0 and "dy_dx" in err()
+    assert fwd(L=0) != 0 and "L must be" in err()
+    assert fwd(C=3) != 0 and "C must be 1, 2, 4, or 8" in err()
+    assert fwd(D=6) != 0 and "C must be 1, 2, 4, or 8" in err()      # the reference's own (mis)wording for D
+    assert fwd(emb=ctypes.c_void_p(0x10004)) != 0 and "aligned" in err()
+    assert l.gcr_grid_encode_backward(None, p, None, p, p, 4, 3, 2, 2, 1.0, 16, 0, None, None, 0, 0, None) != 0
+    assert l.gcr_grid_encode_backward_fused(p, p, None, p, p, 4, 3, 2, 2, 1.0, 16, p, 0, 0, None) != 0
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from gaussiancity_b200 import grid_encoder as ge
+    monkeypatch.setattr(ge, "_lib", None)
+    monkeypatch.setattr(ge, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(ge.GridLibraryError, match="no CPU fallback"):
+        ge.lib()

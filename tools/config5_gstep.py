@@ -22,6 +22,13 @@ staged by oracle/build_ref.py; /root/reference where it exists).  Dependencies o
 import path that this configuration never executes (spconv / torch_scatter / addict / flash_attn
 for PTv3, plyfile for PLY dumps) are stubbed at import time; README.md:152-161 BLDG settings with
 PTV3.ENABLED = False.  Prints one JSON line (rank 0): it/s per rank, loss curve.
+
+SURVEY 8f-4 (hash-grid encoder): `--pos-emd HASH_GRID` switches the generator's positional encoder
+to the reference's GridEncoder (config.py:121-123: 16 levels x 8 channels); `--encoder global` adds
+the reference's GlobalEncoder in front (config.py:118-119: ENCODER_OUT_DIM = 5, the "REST" generator),
+so the grid encoder sees 5 coordinates that require a gradient.  Which `grid_encoder_ext` the
+reference's unmodified extensions/grid_encoder/__init__.py imports follows the arm: the reference
+build (oracle/_ref) for `reference`, ours (gaussiancity_b200/compat) otherwise; `--grid-ext` overrides.
 """
 import argparse
 import json
@@ -33,7 +40,7 @@ import types
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def stage_imports(arm):
+def stage_imports(arm, grid_ext=None):
     ref_root = os.environ.get("GCR_REFERENCE_ROOT")
     if not ref_root:
         ref_root = "/root/reference" if os.path.isdir("/root/reference/models") else \
@@ -64,10 +71,16 @@ def stage_imports(arm):
     # native modules: the reference's grid_encoder_ext (as is) + one of the two rasterizer modules
     native = os.path.join(ROOT, "oracle", "_ref") if arm == "reference" else \
         os.path.join(ROOT, "gaussiancity_b200", "compat")
-    sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))   # grid_encoder_ext
-    sys.path.insert(0, native)                                  # diff_gaussian_rasterization_ext wins from here
+    sys.path.insert(0, native)                                  # diff_gaussian_rasterization_ext
     sys.path.insert(0, ref_root)
     sys.path.insert(1, ROOT)
+    # grid_encoder_ext: loaded by path and registered, so the choice does not depend on sys.path order
+    from tests import refext
+    which = grid_ext or ("reference" if arm == "reference" else "ours")
+    mod = refext.load_reference_grid_ext() if which == "reference" else refext.load_our_grid_ext()
+    if mod is None:
+        raise SystemExit("grid_encoder_ext (%s) is not built" % which)
+    sys.modules["grid_encoder_ext"] = mod
     return ref_root
 
 
@@ -82,6 +95,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--points", type=int, default=16384)
     ap.add_argument("--profile", action="store_true", help="host + device time of the rasterizer calls inside the step")
+    ap.add_argument("--pos-emd", choices=["SIN_COS", "HASH_GRID"], default="SIN_COS")
+    ap.add_argument("--encoder", choices=["none", "global"], default="none")
+    ap.add_argument("--grid-ext", choices=["reference", "ours"], default=None)
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -90,7 +106,7 @@ def main():
     torch.cuda.set_device(dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    ref_root = stage_imports(args.arm)
+    ref_root = stage_imports(args.arm, args.grid_ext)
     import diff_gaussian_rasterization_ext as native_ext
     import models.generator
     import utils.helpers
@@ -98,7 +114,9 @@ def main():
     import numpy as np
 
     # README.md:152-161 (building generator) with PTv3 off; the remaining keys are config.py defaults
-    cfg = Cfg(ENCODER=None, ENCODER_OUT_DIM=3, GLOBAL_ENCODER_N_BLOCKS=6, POS_EMD="SIN_COS",
+    use_global = args.encoder == "global"
+    cfg = Cfg(ENCODER="GLOBAL" if use_global else None, ENCODER_OUT_DIM=5 if use_global else 3,
+              GLOBAL_ENCODER_N_BLOCKS=6, POS_EMD=args.pos_emd,
               HASH_GRID_N_LEVELS=16, HASH_GRID_LEVEL_DIM=8, SIN_COS_FREQ_BENDS=10, Z_DIM=256,
               MLP_HIDDEN_DIM=512, MLP_N_SHARED_LAYERS=1, ATTR_FACTORS={"rgb": 2}, ATTR_N_LAYERS={"rgb": 1},
               PTV3=Cfg(ENABLED=False))
@@ -126,6 +144,11 @@ def main():
     rgb = (torch.rand(1, 3, 448, 640, generator=g) * 2 - 1).to(dev)
     msk = torch.ones(1, 1, 448, 640, device=dev)
     crp = [dict(x=160, y=46, w=640, h=448)]
+    # GlobalEncoder inputs (height field + segmentation map); it mean-pools, so a 256x256 synthetic map
+    # stands in for the 2048x2048 projection without changing what reaches the grid encoder
+    proj_hf = torch.rand(1, 1, 256, 256, generator=g).to(dev) if use_global else None
+    proj_seg = torch.nn.functional.one_hot(torch.randint(0, n_classes, (1, 256, 256), generator=g), n_classes) \
+        .permute(0, 3, 1, 2).float().to(dev) if use_global else None
     cam_pos_b, cam_quat_b = [np.asarray(cam_pos, dtype=np.float32)], [np.asarray(cam_quat, dtype=np.float32)]
 
     ours = None
@@ -161,7 +184,7 @@ def main():
     def step(i):
         torch.manual_seed(5000 + i)      # utils.helpers.get_z draws from the global generator
         z = utils.helpers.get_z(instances, cfg.Z_DIM)
-        pt_attrs = G(proj_uv, rel_xyz, bch_idx, onehots, z, None, None)
+        pt_attrs = G(proj_uv, rel_xyz, bch_idx, onehots, z, proj_hf, proj_seg)
         if args.arm == "ours_fused":   # no [B,N,14] tensor, crop folded into the rasterizer
             fake = adapter.get_gaussian_rasterization_fused(abs_xyz, scales, pt_attrs, gr, cam_pos_b, cam_quat_b, crp)
         else:
@@ -210,7 +233,9 @@ def main():
                           "rasterizer": raster,
                           "rasterizer_module": native_ext.__file__.replace(ROOT + "/", ""),
                           "dgr_python": dgr.__file__.replace(ref_root, "<reference>"),
-                          "generator": "reference models/generator.py, ENCODER=None POS_EMD=SIN_COS Z_DIM=256 PTV3 off"}))
+                          "grid_encoder_module": sys.modules["grid_encoder_ext"].__file__.replace(ROOT + "/", ""),
+                          "generator": f"reference models/generator.py, ENCODER={cfg.ENCODER} POS_EMD={cfg.POS_EMD} "
+                                       "Z_DIM=256 PTV3 off"}))
     if world > 1:
         dist.destroy_process_group()
 
