@@ -14,10 +14,16 @@
  * fused a multiply-add in the reference build (decoded from the SASS of
  * oracle/_ref/grid_encoder_ext*.so): the level scale, the position, the corner accumulation
  * and the derivative accumulation.  The one operation a CPU cannot reproduce bit for bit is
- * exp2f(level * S): the GPU evaluates it with MUFU.EX2 (2 ulp), libm rounds correctly.  For
- * per_level_scale = 2 (S = 1) both are exact; otherwise results agree to ~1e-6 relative and the
- * tests say so.  Pinning: tests/golden/grid/*.npz are outputs of the unmodified reference
- * extension on a B200 (tests/golden/make_golden_grid.py).
+ * exp2f(level * S): the GPU evaluates it with MUFU.EX2 (within 2 ulp), libm rounds correctly; the
+ * `scales` argument takes the level scale from outside for that reason.
+ *
+ * Pinning: tests/golden/grid/*.npz are outputs of the unmodified reference extension on a B200
+ * (tests/golden/make_golden_grid.py, 5 cases: hashed / dense / tiled levels, align_corners,
+ * D = 2..5, C = 1..8, out-of-range points).  With the device's exp2f value (recovered per level
+ * among the 5 floats within 2 ulp of libm's -- exactly one reproduces the level's outputs) the
+ * oracle's outputs, dy_dx and grad_inputs equal the reference's BIT FOR BIT on every case; with
+ * libm's own value they agree to 1e-5 (one ulp of scale at resolution 2000 moves a position by
+ * 1e-4 of a cell).  -> parity is pinned.
  *
  * Sums that the reference forms with atomics (embedding gradients) are formed here in point
  * order per level -- the reference's own order is nondeterministic.
@@ -59,13 +65,15 @@ typedef struct {
     int oob;
 } ggo_site;
 
+/* `scales` (optional, one float per level) replaces ggo_level_scale(): it lets a test hand in the
+ * value the GPU's exp2f produced, the only operation of the path libm does not reproduce bit for bit. */
 static void ggo_locate(ggo_site *s, const float *x, const int *offsets, uint32_t D, uint32_t level, float S,
-                       uint32_t H, int align_corners) {
+                       uint32_t H, int align_corners, const float *scales) {
     s->oob = 0;
     for (uint32_t d = 0; d < D; d++)
         if (x[d] < 0 || x[d] > 1) s->oob = 1;
     s->hashmap_size = (uint32_t)(offsets[level + 1] - offsets[level]);
-    s->scale = ggo_level_scale(level, S, H);
+    s->scale = scales ? scales[level] : ggo_level_scale(level, S, H);
     s->resolution = (uint32_t)ceilf(s->scale) + 1;
     for (uint32_t d = 0; d < D; d++) {
         float pos = fmaf(x[d], s->scale, align_corners ? 0.0f : 0.5f);
@@ -95,14 +103,14 @@ static uint32_t ggo_corner(const ggo_site *s, uint32_t D, uint32_t corner, uint3
 /* kernel_grid: outputs [L,B,C]; dy_dx [B,L,D,C] when calc_grad_inputs. */
 void ggo_forward(const float *inputs, const float *embeddings, const int *offsets, float *outputs, uint32_t B,
                  uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, int calc_grad_inputs, float *dy_dx,
-                 uint32_t gridtype, int align_corners) {
+                 uint32_t gridtype, int align_corners, const float *scales) {
     for (uint32_t level = 0; level < L; level++) {
         const float *table = embeddings + (size_t)(uint32_t)offsets[level] * C;
         for (uint32_t b = 0; b < B; b++) {
             float *out = outputs + ((size_t)level * B + b) * C;
             float *dd = calc_grad_inputs ? dy_dx + ((size_t)b * L + level) * D * C : 0;
             ggo_site s;
-            ggo_locate(&s, inputs + (size_t)b * D, offsets, D, level, S, H, align_corners);
+            ggo_locate(&s, inputs + (size_t)b * D, offsets, D, level, S, H, align_corners, scales);
             if (s.oob) {
                 memset(out, 0, sizeof(float) * C);
                 if (dd) memset(dd, 0, sizeof(float) * D * C);
@@ -146,13 +154,13 @@ void ggo_forward(const float *inputs, const float *embeddings, const int *offset
 /* kernel_grid_backward: grad [L,B,C] scattered into grad_embeddings (accumulated, caller zeroes). */
 void ggo_backward_grid(const float *grad, const float *inputs, const int *offsets, float *grad_embeddings,
                        uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, uint32_t gridtype,
-                       int align_corners) {
+                       int align_corners, const float *scales) {
     for (uint32_t level = 0; level < L; level++) {
         float *table = grad_embeddings + (size_t)(uint32_t)offsets[level] * C;
         for (uint32_t b = 0; b < B; b++) {
             const float *g = grad + ((size_t)level * B + b) * C;
             ggo_site s;
-            ggo_locate(&s, inputs + (size_t)b * D, offsets, D, level, S, H, align_corners);
+            ggo_locate(&s, inputs + (size_t)b * D, offsets, D, level, S, H, align_corners, scales);
             if (s.oob) continue;
             for (uint32_t corner = 0; corner < (1u << D); corner++) {
                 float w;
@@ -179,11 +187,12 @@ void ggo_backward_input(const float *grad, const float *dy_dx, float *grad_input
 /* Test helper: the table row (within its level) of every corner of every (level, point):
  * rows [L,B,2^D] uint32, weights [L,B,2^D] -- lets a test compare integer work exactly. */
 void ggo_corner_rows(const float *inputs, const int *offsets, uint32_t *rows, float *weights, uint32_t B,
-                     uint32_t D, uint32_t L, float S, uint32_t H, uint32_t gridtype, int align_corners) {
+                     uint32_t D, uint32_t L, float S, uint32_t H, uint32_t gridtype, int align_corners,
+                     const float *scales) {
     for (uint32_t level = 0; level < L; level++)
         for (uint32_t b = 0; b < B; b++) {
             ggo_site s;
-            ggo_locate(&s, inputs + (size_t)b * D, offsets, D, level, S, H, align_corners);
+            ggo_locate(&s, inputs + (size_t)b * D, offsets, D, level, S, H, align_corners, scales);
             for (uint32_t corner = 0; corner < (1u << D); corner++) {
                 size_t o = (((size_t)level * B + b) << D) + corner;
                 rows[o] = ggo_corner(&s, D, corner, gridtype, align_corners, &weights[o]);

@@ -63,9 +63,28 @@ def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
+def _scales(scales, L):
+    if scales is None:
+        return None, None
+    a = _f32(scales).reshape(-1)
+    assert a.shape[0] == L
+    return a, _p(a)
+
+
+def level_scale(level, per_level_scale, base_resolution, exp2_ulps=0):
+    """fma(exp2f(level * S), H, -1) as the oracle evaluates it; `exp2_ulps` moves the exp2f result by
+    that many float steps (the GPU's MUFU.EX2 is within 2 ulp of libm's correctly rounded value)."""
+    S = np.float32(math.log2(per_level_scale))
+    e = np.float32(np.exp2(np.float32(level) * S))
+    for _ in range(abs(exp2_ulps)):
+        e = np.nextafter(e, np.float32(np.inf if exp2_ulps > 0 else -np.inf), dtype=np.float32)
+    return np.float32(float(e) * float(base_resolution) - 1.0)
+
+
 def forward(inputs, embeddings, offsets, per_level_scale, base_resolution, calc_grad_inputs=False, gridtype=0,
-            align_corners=False):
-    """kernel_grid.  Returns (outputs [L,B,C], dy_dx [B,L*D*C] or None)."""
+            align_corners=False, scales=None):
+    """kernel_grid.  Returns (outputs [L,B,C], dy_dx [B,L*D*C] or None).  `scales`: optional per-level
+    override of the level scale (see grid_oracle.c)."""
     inputs, embeddings = _f32(inputs), _f32(embeddings)
     offsets = np.ascontiguousarray(offsets, dtype=np.int32)
     B, D = inputs.shape
@@ -73,15 +92,16 @@ def forward(inputs, embeddings, offsets, per_level_scale, base_resolution, calc_
     S = math.log2(per_level_scale)
     out = np.empty((L, B, C), np.float32)
     dy_dx = np.empty((B, L * D * C), np.float32) if calc_grad_inputs else None
+    sc, sc_p = _scales(scales, L)
     lib().ggo_forward(_p(inputs), _p(embeddings), _p(offsets), _p(out), ctypes.c_uint32(B), ctypes.c_uint32(D),
                       ctypes.c_uint32(C), ctypes.c_uint32(L), ctypes.c_float(S), ctypes.c_uint32(base_resolution),
                       ctypes.c_int(1 if calc_grad_inputs else 0), _p(dy_dx) if calc_grad_inputs else None,
-                      ctypes.c_uint32(gridtype), ctypes.c_int(1 if align_corners else 0))
+                      ctypes.c_uint32(gridtype), ctypes.c_int(1 if align_corners else 0), sc_p)
     return out, dy_dx
 
 
 def backward(grad, inputs, n_embeddings, offsets, per_level_scale, base_resolution, dy_dx=None, gridtype=0,
-             align_corners=False):
+             align_corners=False, scales=None):
     """kernel_grid_backward (+ kernel_input_backward when dy_dx is given).  grad is [L,B,C].
     Returns (grad_embeddings [sO,C], grad_inputs [B,D] or None)."""
     grad, inputs = _f32(grad), _f32(inputs)
@@ -90,10 +110,11 @@ def backward(grad, inputs, n_embeddings, offsets, per_level_scale, base_resoluti
     D = inputs.shape[1]
     S = math.log2(per_level_scale)
     ge = np.zeros((n_embeddings, C), np.float32)
+    sc, sc_p = _scales(scales, L)
     lib().ggo_backward_grid(_p(grad), _p(inputs), _p(offsets), _p(ge), ctypes.c_uint32(B), ctypes.c_uint32(D),
                             ctypes.c_uint32(C), ctypes.c_uint32(L), ctypes.c_float(S),
                             ctypes.c_uint32(base_resolution), ctypes.c_uint32(gridtype),
-                            ctypes.c_int(1 if align_corners else 0))
+                            ctypes.c_int(1 if align_corners else 0), sc_p)
     gi = None
     if dy_dx is not None:
         dy_dx = _f32(dy_dx)
@@ -103,7 +124,7 @@ def backward(grad, inputs, n_embeddings, offsets, per_level_scale, base_resoluti
     return ge, gi
 
 
-def corner_rows(inputs, offsets, per_level_scale, base_resolution, gridtype=0, align_corners=False):
+def corner_rows(inputs, offsets, per_level_scale, base_resolution, gridtype=0, align_corners=False, scales=None):
     """Integer work only: table row of each of the 2^D corners, [L,B,2^D] uint32, and their weights."""
     inputs = _f32(inputs)
     offsets = np.ascontiguousarray(offsets, dtype=np.int32)
@@ -111,10 +132,11 @@ def corner_rows(inputs, offsets, per_level_scale, base_resolution, gridtype=0, a
     L = offsets.shape[0] - 1
     rows = np.empty((L, B, 1 << D), np.uint32)
     w = np.empty((L, B, 1 << D), np.float32)
+    sc, sc_p = _scales(scales, L)
     lib().ggo_corner_rows(_p(inputs), _p(offsets), _p(rows), _p(w), ctypes.c_uint32(B), ctypes.c_uint32(D),
                           ctypes.c_uint32(L), ctypes.c_float(math.log2(per_level_scale)),
                           ctypes.c_uint32(base_resolution), ctypes.c_uint32(gridtype),
-                          ctypes.c_int(1 if align_corners else 0))
+                          ctypes.c_int(1 if align_corners else 0), sc_p)
     return rows, w
 
 

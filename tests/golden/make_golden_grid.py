@@ -66,6 +66,11 @@ def main(outdir):
         xm = (x * 2 - 1).clone().requires_grad_(True)
         ym = enc(xm)
         torch.cuda.synchronize()
+        # the device's own exp2f(level * S) (same CUDA libm routine the kernels call: MUFU.EX2 based), so the
+        # CPU oracle can be handed the exact level scale instead of recovering it (test_grid_encoder_cpu.py)
+        lv = torch.arange(L, device=dev, dtype=torch.float32) * torch.tensor(S, dtype=torch.float32, device=dev)
+        e = torch.exp2(lv).cpu().numpy().astype(np.float64)
+        level_scales = (e * float(c["H"]) - 1.0).astype(np.float32)
         np.savez_compressed(
             os.path.join(outdir, name + ".npz"),
             inputs=x.cpu().numpy(), embeddings=enc.embeddings.data.cpu().numpy(),
@@ -74,7 +79,8 @@ def main(outdir):
             log2_hashmap_size=np.int32(c["log2T"]), gridtype=np.int32(enc.gridtype_id),
             align_corners=np.int32(1 if c["align"] else 0), outputs=outputs.cpu().numpy(),
             dy_dx=dy_dx.cpu().numpy(), grad=grad.cpu().numpy(), grad_embeddings=ge.cpu().numpy(),
-            grad_inputs=gi.cpu().numpy(), module_outputs=ym.detach().cpu().numpy())
+            grad_inputs=gi.cpu().numpy(), module_outputs=ym.detach().cpu().numpy(),
+            level_scales_torch_exp2=level_scales)
         print(name, "outputs", tuple(outputs.shape), "table rows", int(enc.offsets[-1]))
 
 

