@@ -48,6 +48,9 @@ def main(argv=None):
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--once", action="store_true")
+    ap.add_argument("--fused", action="store_true",
+                    help="also time ours with backward_fused (no dy_dx tensor: forward without the derivative, one "
+                         "backward launch that re-reads the corner rows)")
     args = ap.parse_args(argv)
     import torch
     from tests import refext
@@ -80,13 +83,24 @@ def main(argv=None):
     gemb = torch.empty_like(emb)
     gin = torch.empty(B, D, device=dev)
 
+    class Fused:          # ours through gcr_grid_encode_backward_fused: same results, no [B, L, D, C] tensor
+        pass
+    if args.fused and "ours" in arms:
+        arms["ours_fused"] = Fused
+
     def fwd(ext):
-        ext.forward(x, emb, offsets, outputs, B, D, C, L, S, H, True, dy_dx, 0, False)
+        if ext is Fused:
+            ge.grid_encoder_ext.forward(x, emb, offsets, outputs, B, D, C, L, S, H, False, dy_dx, 0, False)
+        else:
+            ext.forward(x, emb, offsets, outputs, B, D, C, L, S, H, True, dy_dx, 0, False)
 
     def bwd(ext):
         gemb.zero_()
         gin.zero_()
-        ext.backward(grad, x, emb, offsets, gemb, B, D, C, L, S, H, True, dy_dx, gin, 0, False)
+        if ext is Fused:
+            ge.grid_encoder_ext.backward_fused(grad, x, emb, offsets, gemb, B, D, C, L, S, H, gin, 0, False)
+        else:
+            ext.backward(grad, x, emb, offsets, gemb, B, D, C, L, S, H, True, dy_dx, gin, 0, False)
 
     results = {}
     for name, ext in arms.items():
@@ -95,9 +109,14 @@ def main(argv=None):
         torch.cuda.synchronize()
         results[name] = (outputs.clone(), dy_dx.clone(), gemb.clone(), gin.clone())
     parity = None
-    if len(results) == 2:
+    rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm())
+    fused_parity = None
+    if "ours_fused" in results:
+        o, f = results["ours"], results["ours_fused"]
+        fused_parity = {"outputs_bit_exact": bool(torch.equal(o[0], f[0])), "grad_inputs_relerr": rel(f[3], o[3]),
+                        "grad_embeddings_relerr": rel(f[2], o[2])}
+    if "ours" in results and "reference" in results:
         o, r = results["ours"], results["reference"]
-        rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm())
         parity = {"outputs_bit_exact": bool(torch.equal(o[0], r[0])), "dy_dx_bit_exact": bool(torch.equal(o[1], r[1])),
                   "grad_inputs_bit_exact": bool(torch.equal(o[3], r[3])), "grad_embeddings_relerr": rel(o[2], r[2])}
     if args.once:
@@ -157,6 +176,8 @@ def main(argv=None):
                                       "frac": bwd_bytes / (ms_b * 1e-3) / 1e9 / peak}},
             "parity_vs_reference": parity, "vs_baseline": None,
         }
+        if name == "ours_fused":
+            line["parity_vs_two_pass"] = fused_parity
         if name == "ours" and not args.no_cpu_baseline:
             from oracle import grid_oracle as go
             n = min(B, 2048)

@@ -163,9 +163,15 @@ class GridEncoderFunction(torch.autograd.Function):
     """extensions/grid_encoder/__init__.py:19-124, same positional arguments (+ fused_backward)."""
 
     @staticmethod
-    def forward(ctx, inputs, embeddings, offsets, per_level_scale, base_resolution, calc_grad_inputs=False,
-                gridtype=0, align_corners=False, fused_backward=False):
+    def forward(ctx, inputs, embeddings, offsets, per_level_scale, base_resolution, *optional):
         # inputs [B, D] in [0, 1]; embeddings [sO, C]; offsets [L + 1] int32; returns [B, L * C]
+        # optional, positional like the reference: calc_grad_inputs=False, gridtype=0, align_corners=False
+        # (+ fused_backward=False); autograd wants one gradient per argument actually passed
+        if len(optional) > 4:
+            raise TypeError("GridEncoderFunction takes at most 9 arguments")
+        calc_grad_inputs, gridtype, align_corners, fused_backward = \
+            tuple(optional) + (False, 0, False, False)[len(optional):]
+        ctx.n_optional = len(optional)
         inputs = inputs.contiguous()
         B, D = inputs.shape
         L = offsets.shape[0] - 1
@@ -206,10 +212,11 @@ class GridEncoderFunction(torch.autograd.Function):
         else:
             grid_encoder_ext.backward(grad, inputs, embeddings, offsets, grad_embeddings, B, D, C, L, S, H,
                                       calc_grad_inputs, dy_dx, grad_inputs, gridtype, align_corners)
+        none = (None,) * (3 + ctx.n_optional)
         if calc_grad_inputs:
             grad_inputs = grad_inputs.to(inputs.dtype)
-            return grad_inputs, grad_embeddings, None, None, None, None, None, None, None
-        return None, grad_embeddings, None, None, None, None, None, None, None
+            return (grad_inputs, grad_embeddings) + none
+        return (None, grad_embeddings) + none
 
 
 def level_offsets(in_channels, n_levels, base_resolution=16, per_level_scale=2, log2_hashmap_size=19,

@@ -243,3 +243,44 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(ge, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(ge.GridLibraryError, match="no CPU fallback"):
         ge.lib()
+
+
+def test_autograd_function_returns_one_gradient_per_argument(monkeypatch):
+    """GridEncoderFunction.apply is called with 5..9 positional arguments (the reference's module passes 8,
+    ours 9); autograd insists on exactly one gradient per argument.  Host plumbing only: the native
+    binding is replaced by a recorder, no device work."""
+    from gaussiancity_b200 import grid_encoder as ge
+    calls = []
+
+    class Recorder:
+        @staticmethod
+        def forward(inputs, emb, offs, out, B, D, C, L, S, H, calc, dy_dx, gridtype, align):
+            calls.append(("fwd", B, D, C, L, bool(calc), tuple(dy_dx.shape), gridtype, bool(align)))
+            out.zero_()
+
+        @staticmethod
+        def backward(grad, inputs, emb, offs, gemb, B, D, C, L, S, H, calc, dy_dx, gin, gridtype, align):
+            calls.append(("bwd", tuple(grad.shape), bool(calc), tuple(gin.shape)))
+
+        @staticmethod
+        def backward_fused(grad, inputs, emb, offs, gemb, B, D, C, L, S, H, gin, gridtype, align):
+            calls.append(("bwd_fused", tuple(grad.shape), tuple(gin.shape)))
+
+    monkeypatch.setattr(ge, "grid_encoder_ext", Recorder)
+    offs = torch.tensor([0, 32, 64], dtype=torch.int32)
+    for extra in [(), (True,), (True, 0), (True, 1, True), (True, 0, False, True), (False, 0, False, True)]:
+        calls.clear()
+        x = torch.rand(4, 3, requires_grad=True)
+        E = torch.rand(64, 2, requires_grad=True)
+        y = ge.GridEncoderFunction.apply(x, E, offs, 2.0, 16, *extra)
+        assert y.shape == (4, 2 * 2)
+        y.sum().backward()
+        calc = bool(extra[0]) if extra else False
+        fused = len(extra) == 4 and extra[3]
+        assert (x.grad is not None) == calc and E.grad is not None and E.grad.shape == E.shape
+        # the derivative tensor exists only on the two-pass path
+        assert calls[0][:6] == ("fwd", 4, 3, 2, 2, calc and not fused)
+        assert calls[0][6] == ((4, 2 * 3 * 2) if calc and not fused else (1,))
+        assert calls[1][0] == ("bwd_fused" if calc and fused else "bwd") and calls[1][1] == (2, 4, 2)
+    with pytest.raises(TypeError):
+        ge.GridEncoderFunction.apply(torch.rand(4, 3), torch.rand(64, 2), offs, 2.0, 16, False, 0, False, False, 1)
