@@ -36,6 +36,7 @@ EXPORTED_SYMBOLS = (
     "gcr_profile_stage_count",
     "gcr_profile_stage_name",
     "gcr_profile_stage_ms",
+    "gcr_set_programmatic_launch",
 )
 
 # enum values of gcr_debug_offset (include/gcr_rasterizer.h)
@@ -111,6 +112,8 @@ def _declare(l):
     l.gcr_profile_stage_name.argtypes = [c_int]
     l.gcr_profile_stage_ms.restype = c_float
     l.gcr_profile_stage_ms.argtypes = [c_int]
+    l.gcr_set_programmatic_launch.restype = c_int
+    l.gcr_set_programmatic_launch.argtypes = [c_int]
 
 
 def lib():
@@ -143,6 +146,12 @@ def check(rc, what):
     if rc < 0:
         raise RuntimeError(f"{what}: {last_error()}")
     return rc
+
+
+def set_programmatic_launch(on):
+    """Programmatic dependent launch of the frame's kernel chain (include/gcr_rasterizer.h); returns the
+    previous setting."""
+    return bool(lib().gcr_set_programmatic_launch(1 if on else 0))
 
 
 def profile_enable(on=True):

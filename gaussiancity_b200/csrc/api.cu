@@ -27,6 +27,21 @@
 
 static_assert(GCR_MAX_SHARDS == GCR_MAX_RANKS, "public and internal stripe limits must agree");
 
+// Programmatic dependent launch of the kernel chain (gcr_common.cuh): process-wide switch, initial
+// value from GCR_PDL (0 / 1) when set.
+#ifndef GCR_PDL_DEFAULT
+#define GCR_PDL_DEFAULT 0
+#endif
+static std::atomic<int>& pdl_flag() {
+  static std::atomic<int> flag{[] {
+    const char* e = getenv("GCR_PDL");
+    return e != nullptr ? (e[0] != '0' ? 1 : 0) : GCR_PDL_DEFAULT;
+  }()};
+  return flag;
+}
+bool gcr_pdl_enabled() { return pdl_flag().load(std::memory_order_relaxed) != 0; }
+
+
 namespace {
 
 thread_local std::string g_last_error;
@@ -834,6 +849,8 @@ int gcr_peer_barrier(void* const* flag_arrays, int rank, int world, unsigned int
 }
 
 void gcr_debug_set_cov3d_out(float* cov3d) { g_dbg_cov3d = cov3d; }
+
+int gcr_set_programmatic_launch(int on) { return pdl_flag().exchange(on != 0 ? 1 : 0); }
 
 void gcr_profile_enable(int on) {
   g_prof.enabled = on != 0;

@@ -100,6 +100,8 @@ radix_hist_all_kernel(const uint32_t* __restrict__ keys, uint32_t n_max,
   constexpr int kItems = 16;
   constexpr int kChunk = kSortThreads * kItems;
   __shared__ uint32_t hist[kMaxPasses][kBins];
+  gcr_pdl_wait();
+  gcr_pdl_trigger();
 #pragma unroll
   for (int p = 0; p < kMaxPasses; ++p) hist[p][threadIdx.x] = 0;
   __syncthreads();
@@ -152,6 +154,8 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
   constexpr int kWarps = kThreads / 32;
   constexpr int kTile = kThreads * kItems;
   extern __shared__ __align__(16) uint32_t os_smem[];
+  gcr_pdl_wait();
+  gcr_pdl_trigger();
   uint32_t (*warp_hist)[kBins] = reinterpret_cast<uint32_t (*)[kBins]>(os_smem);
   uint32_t* gbase = os_smem + kWarps * kBins;
   uint32_t* bstart = gbase + kBins;
@@ -290,9 +294,8 @@ cudaError_t launch_onesweep_pass(unsigned tiles, cudaStream_t stream, const uint
   static std::atomic<unsigned long long> configured{0ull};   // one per template instance
   cudaError_t e = gcr_set_dynamic_smem_once(onesweep_pass_kernel<kFirstDepth, kThreads, kItems>, smem, configured);
   if (e != cudaSuccess) return e;
-  onesweep_pass_kernel<kFirstDepth, kThreads, kItems><<<tiles, kThreads, smem, stream>>>(
-      kin, vin, kout, vout, n_max, n_ptr, shift, mask, bits, ghist, st, ticket, n_out);
-  return cudaGetLastError();
+  return gcr_launch_chain(onesweep_pass_kernel<kFirstDepth, kThreads, kItems>, dim3(tiles), dim3(kThreads), smem, stream,
+                          kin, vin, kout, vout, n_max, n_ptr, shift, mask, bits, ghist, st, ticket, n_out);
 }
 
 constexpr size_t kSmallTileMaxN = 262144;   // up to here the 1024-pair tiles are used
@@ -343,6 +346,8 @@ emit_scan_kernel(EmitArgs a) {
   __shared__ uint64_t s_excl;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int npass = (a.tile_end_bit + 7) / 8;
+  gcr_pdl_wait();
+  gcr_pdl_trigger();
 #pragma unroll
   for (int p = 0; p < kMaxPasses; ++p) hist[p][tid] = 0;
   const uint32_t n_vis = load_count(a.n_vis, a.n_max);
@@ -477,6 +482,8 @@ emit_scan_kernel(EmitArgs a) {
 __global__ void __launch_bounds__(256)
 tile_ranges_kernel(uint32_t n_max, const uint32_t* __restrict__ n_ptr,
                    const uint32_t* __restrict__ keys, uint2* __restrict__ ranges) {
+  gcr_pdl_wait();
+  gcr_pdl_trigger();
   const uint32_t R = load_count(n_ptr, n_max);
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < R; i += stride) {
@@ -528,8 +535,8 @@ cudaError_t gcr_launch_radix_sort(uint32_t* keys_in, uint32_t* vals_in, uint32_t
   if (!hist_done) {
     const size_t chunks = (n_max + 4095) / 4096;
     const unsigned hgrid = (unsigned)(chunks < (size_t)148 * 8 ? chunks : (size_t)148 * 8);
-    radix_hist_all_kernel<<<hgrid, kSortThreads, 0, stream>>>(keys_in, n32, n_ptr, end_bit, depth_mode, ghist);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = gcr_launch_chain(radix_hist_all_kernel, dim3(hgrid), dim3(kSortThreads), 0, stream, keys_in, n32,
+                                     n_ptr, end_bit, depth_mode, ghist);
     if (e != cudaSuccess) return e;
   }
   uint32_t* kin = keys_in; uint32_t* vin = vals_in; uint32_t* kout = keys_out; uint32_t* vout = vals_out;
@@ -571,14 +578,13 @@ cudaError_t gcr_launch_emit_scan(const GcrEmitLaunch& l, cudaStream_t stream) {
   a.counters = l.counters; a.offsets_out = l.offsets_out;
   const unsigned chunks = (l.n_max + kEmitThreads - 1) / kEmitThreads;
   const unsigned grid = chunks < 148u * 8u ? chunks : 148u * 8u;   // persistent: 8 CTAs per SM
-  emit_scan_kernel<<<grid, kEmitThreads, 0, stream>>>(a);
-  return cudaGetLastError();
+  return gcr_launch_chain(emit_scan_kernel, dim3(grid), dim3(kEmitThreads), 0, stream, a);
 }
 
 cudaError_t gcr_launch_tile_ranges(uint32_t n_max, const uint32_t* n_ptr, const uint32_t* sorted_keys,
                                    uint2* ranges, cudaStream_t stream) {
   if (n_max == 0) return cudaSuccess;
   const unsigned blocks = (n_max + 255) / 256;
-  tile_ranges_kernel<<<blocks < 148u * 16u ? blocks : 148u * 16u, 256, 0, stream>>>(n_max, n_ptr, sorted_keys, ranges);
-  return cudaGetLastError();
+  return gcr_launch_chain(tile_ranges_kernel, dim3(blocks < 148u * 16u ? blocks : 148u * 16u), dim3(256), 0, stream,
+                          n_max, n_ptr, sorted_keys, ranges);
 }

@@ -50,6 +50,8 @@ constexpr int kOwnerShift = 27;   // striped frames: owner rank in the top 5 bit
 __global__ void __launch_bounds__(kBlendThreads, 4)   // 64 registers: 4 CTAs/SM (shared memory allows 4)
 blend_bwd_kernel(GcrBlendArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  gcr_pdl_wait();
+  gcr_pdl_trigger();
   GcrRecord (*stage)[kBlendBatch] = reinterpret_cast<GcrRecord (*)[kBlendBatch]>(smem_raw);
   unsigned char* scratch0 = smem_raw + kBlendStages * kBlendBatch * sizeof(GcrRecord);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(scratch0 + 8 * kWarpScratchBytes);
@@ -308,6 +310,5 @@ cudaError_t gcr_launch_blend_bwd(const GcrBlendArgs& a, cudaStream_t stream) {
   static std::atomic<unsigned long long> configured{0ull};
   cudaError_t e = gcr_set_dynamic_smem_once(blend_bwd_kernel, kBwdSmemBytes, configured);
   if (e != cudaSuccess) return e;
-  blend_bwd_kernel<<<grid, kBlendThreads, kBwdSmemBytes, stream>>>(a);
-  return cudaGetLastError();
+  return gcr_launch_chain(blend_bwd_kernel, grid, dim3(kBlendThreads), kBwdSmemBytes, stream, a);
 }

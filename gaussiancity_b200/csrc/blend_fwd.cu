@@ -30,6 +30,8 @@ blend_fwd_kernel(GcrBlendArgs a) {
   __shared__ __align__(128) GcrRecord stage[kBlendStages][kBlendBatch];
   __shared__ __align__(8) uint64_t full_bar[kBlendStages];
   __shared__ int vote[3];
+  gcr_pdl_wait();
+  gcr_pdl_trigger();
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile_x = a.tile_x0 + (int)blockIdx.x;
@@ -159,6 +161,5 @@ blend_fwd_kernel(GcrBlendArgs a) {
 cudaError_t gcr_launch_blend_fwd(const GcrBlendArgs& a, cudaStream_t stream) {
   if (a.tiles_x <= 0 || a.tiles_y <= 0) return cudaSuccess;
   dim3 grid(a.tiles_x, a.stripe != nullptr ? a.grid_y : a.tiles_y, 1);
-  blend_fwd_kernel<<<grid, kBlendThreads, 0, stream>>>(a);
-  return cudaGetLastError();
+  return gcr_launch_chain(blend_fwd_kernel, grid, dim3(kBlendThreads), 0, stream, a);
 }

@@ -165,6 +165,16 @@ __forceinline__ __device__ void gcr_stg_v8(float* p, const float (&v)[8]) {
                : "memory");
 }
 
+// Programmatic dependent launch (PDL).  A frame of GaussianCity's own size (<= 16 384 points) is a chain
+// of ~13 dependent kernels of 4-10 us each, so launch latency between them is a fifth of the frame.
+// Kernels of the chain start with gcr_pdl_wait() -- everything the predecessor wrote is visible after it;
+// a no-op when the kernel was launched the ordinary way -- followed by gcr_pdl_trigger(), which lets the
+// NEXT kernel of the stream be scheduled (its CTAs then sit in their own gcr_pdl_wait()) as soon as every
+// CTA of this one has started.  Since every kernel of a chain waits before touching memory, completion
+// stays transitive: a kernel that has finished implies all its predecessors have.
+__forceinline__ __device__ void gcr_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__forceinline__ __device__ void gcr_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 static inline size_t gcr_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // Opt-in dynamic shared-memory size: a per-device function attribute that costs microseconds to
@@ -182,5 +192,23 @@ static inline cudaError_t gcr_set_dynamic_smem_once(Kernel kernel, int bytes, st
   e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e == cudaSuccess && bit != 0ull) mask.fetch_or(bit, std::memory_order_release);
   return e;
+}
+
+// <<<>>> with the programmatic-stream-serialization attribute when PDL is on (gcr_pdl_enabled(), api.cu).
+bool gcr_pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t gcr_launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                           cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = gcr_pdl_enabled() ? 1u : 0u;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 #endif

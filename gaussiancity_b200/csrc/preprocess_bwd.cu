@@ -408,6 +408,7 @@ preprocess_bwd_kernel(GcrPreprocessBwdArgs a) {
   __shared__ uint32_t queue[kChunk + 256];
   __shared__ uint32_t wcount[kItems][8];
   __shared__ int s_chunk;
+  gcr_pdl_wait();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nchunks = (a.range_count + kChunk - 1) / kChunk;
   uint32_t pending = 0;   // block-uniform: entries in the queue
@@ -480,12 +481,8 @@ cudaError_t gcr_launch_preprocess_bwd(const GcrPreprocessBwdArgs& a, cudaStream_
   const int chunk = big ? 2048 : 256;
   const int chunks = (a.range_count + chunk - 1) / chunk;
   const int blocks = chunks < 148 * 4 ? chunks : 148 * 4;
-  if (big) {
-    if (sh) preprocess_bwd_kernel<true, 8><<<blocks, 256, 0, stream>>>(a);
-    else preprocess_bwd_kernel<false, 8><<<blocks, 256, 0, stream>>>(a);
-  } else {
-    if (sh) preprocess_bwd_kernel<true, 1><<<blocks, 256, 0, stream>>>(a);
-    else preprocess_bwd_kernel<false, 1><<<blocks, 256, 0, stream>>>(a);
-  }
-  return cudaGetLastError();
+  void (*kernel)(GcrPreprocessBwdArgs) =
+      big ? (sh ? preprocess_bwd_kernel<true, 8> : preprocess_bwd_kernel<false, 8>)
+          : (sh ? preprocess_bwd_kernel<true, 1> : preprocess_bwd_kernel<false, 1>);
+  return gcr_launch_chain(kernel, dim3(blocks), dim3(256), 0, stream, a);
 }

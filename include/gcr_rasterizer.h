@@ -258,6 +258,15 @@ GCR_API int gcr_profile_stage_count(void);
 GCR_API const char* gcr_profile_stage_name(int stage);
 GCR_API float gcr_profile_stage_ms(int stage);
 
+/* ---- programmatic dependent launch ------------------------------------------------------------
+ * The dependent kernels of a frame (sort passes, scan + emit, tile ranges, both blends, geometry
+ * backward) can be launched with CUDA's programmatic stream serialization: each starts with
+ * griddepcontrol.wait, so results are unchanged, and the launch latency between them overlaps
+ * the predecessor's tail -- what matters for frames of GaussianCity's own size (<= 16 384 points,
+ * 13 kernels of 4-10 us).  Process-wide; on = 1 / off = 0; returns the previous setting.  The
+ * initial value is GCR_PDL from the environment when set (0 / 1), else GCR_PDL_DEFAULT. */
+GCR_API int gcr_set_programmatic_launch(int on);
+
 #ifdef __cplusplus
 }
 #endif

@@ -336,3 +336,37 @@ def test_non_contiguous_and_offset_inputs(built_lib, cuda_device):
                                  64, 96, e, 0, s.campos, False, False)
     b = ours.rasterize_gaussians(*refext.scene_forward_args(s))
     assert a[0] == b[0] and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+
+
+def test_launch_modes_agree_on_small_frames(built_lib, cuda_device):
+    """GaussianCity's own regime (16 384 points, 960x540: 13 dependent kernels of a few microseconds)
+    rendered 25 times back to back in each launch mode -- ordinary stream order and programmatic dependent
+    launch (gcr_set_programmatic_launch): every frame bit-identical to the first, in both modes, and the
+    gradients of the two modes agree to float-reduction order.  A kernel that read its predecessor's
+    output too early would show up here as a frame that differs."""
+    from gaussiancity_b200 import _cabi
+    rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+    pts, cam_pos, cam_quat = city_points(16_384, seed=31, device=cuda_device)
+    wrap = g.GaussianRasterizerWrapper(CITY_K, CITY_SENSOR, device=cuda_device)
+    G = torch.randn(3, 540, 960, generator=torch.Generator().manual_seed(8)).to(cuda_device)
+    prev = _cabi.set_programmatic_launch(False)
+    frames, grads = {}, {}
+    try:
+        for mode in (False, True):
+            _cabi.set_programmatic_launch(mode)
+            first = None
+            for it in range(25):
+                p = pts.clone().requires_grad_(True)
+                img = wrap(p, cam_pos, cam_quat)
+                (img * G).sum().backward()
+                if first is None:
+                    first, grads[mode] = img.detach().clone(), p.grad.clone()
+                else:
+                    assert torch.equal(img.detach(), first), f"PDL={mode}: frame {it} differs from frame 0"
+                    assert rel(p.grad, grads[mode]) < 1e-5
+            frames[mode] = first
+        torch.cuda.synchronize()
+    finally:
+        _cabi.set_programmatic_launch(prev)
+    assert torch.equal(frames[False], frames[True])
+    assert rel(grads[True], grads[False]) < 1e-5

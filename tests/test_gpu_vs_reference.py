@@ -56,6 +56,28 @@ def _relerr(a, b):
 
 @pytest.mark.parametrize("name,P,W,H,deg,use_sh,seed", CONFIGS, ids=[c[0] for c in CONFIGS])
 def test_forward_backward_match_reference(ref, built_lib, cuda_device, name, P, W, H, deg, use_sh, seed):
+    _check_against_reference(ref, cuda_device, name, P, W, H, deg, use_sh, seed)
+
+
+PDL_CONFIGS = [c for c in CONFIGS if c[0] in ("tiny_precomp", "ragged_sh3", "cfg2_100k_sh0", "cfg3_1M_sh3")]
+
+
+@pytest.mark.parametrize("name,P,W,H,deg,use_sh,seed", PDL_CONFIGS, ids=[c[0] for c in PDL_CONFIGS])
+def test_other_launch_mode_matches_reference(ref, built_lib, cuda_device, name, P, W, H, deg, use_sh, seed):
+    """The frame's dependent kernels launched the OTHER way round -- programmatic dependent launch
+    (gcr_set_programmatic_launch, include/gcr_rasterizer.h) when the default is ordinary stream order, and
+    vice versa: same bars, bit-exact forward, so both launch modes of the library are covered."""
+    from gaussiancity_b200 import _cabi
+    prev = _cabi.set_programmatic_launch(True)
+    _cabi.set_programmatic_launch(not prev)
+    try:
+        for _ in range(3 if P <= 100_000 else 1):     # small frames: where the overlap is widest
+            _check_against_reference(ref, cuda_device, name, P, W, H, deg, use_sh, seed)
+    finally:
+        _cabi.set_programmatic_launch(prev)
+
+
+def _check_against_reference(ref, cuda_device, name, P, W, H, deg, use_sh, seed):
     s = uniform_scene(P, W, H, sh_degree=deg, seed=seed, device=cuda_device, use_sh=use_sh,
                       bg=(0.1, 0.2, 0.3))
     args = refext.scene_forward_args(s)
