@@ -37,6 +37,46 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
 
 
+def run_e2e(name, torch, ge, refext, x_host, emb, D, C, L, steps, warmup, dev):
+    """The same step through the public module surface with HOST inputs: pinned [B, D] coordinates in
+    [-1, 1] copied H2D every step, GridEncoder.forward (maps to [0, 1], encodes), a scalar loss, backward
+    to the table and the inputs, the encoding [B, L*C] and the loss read back to pinned host memory."""
+    if name == "reference":
+        py = refext.load_reference_grid_python(refext.load_reference_grid_ext(), "ref_grid_py_bench")
+        enc = py.GridEncoder(in_channels=D, n_levels=L, lvl_channels=C, desired_resolution=2048).to(dev)
+    else:
+        enc = ge.GridEncoder(in_channels=D, n_levels=L, lvl_channels=C, desired_resolution=2048,
+                             fused_backward=(name == "ours_fused")).to(dev)
+    with torch.no_grad():
+        enc.embeddings.copy_(emb)
+    B = x_host.shape[0]
+    out_host = torch.empty(B, L * C).pin_memory()
+    loss_host = torch.empty(1).pin_memory()
+    w = torch.randn(B, L * C, device=dev)
+
+    def step():
+        x = x_host.to(dev, non_blocking=True).requires_grad_(True)
+        y = enc(x)
+        loss = (y * w).sum()
+        enc.embeddings.grad = None
+        loss.backward()
+        out_host.copy_(y.detach(), non_blocking=True)
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"value": B / ms / 1e3, "unit": "Mpoints/s", "ms_per_step": ms, "h2d_bytes_per_step": int(x_host.numel() * 4),
+            "d2h_bytes_per_step": int(out_host.numel() * 4 + 4),
+            "note": "GridEncoder module (public API), autograd fwd+bwd incl. the torch ops around the kernels"}
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--impl", default="both", choices=["ours", "reference", "both"])
@@ -55,7 +95,9 @@ def main(argv=None):
     import torch
     from tests import refext
     from gaussiancity_b200 import grid_encoder as ge
-    assert torch.cuda.is_available(), "needs a CUDA device (there is no CPU path)"
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: this benchmark has no CPU path"}))
+        sys.exit(1)
     dev = torch.device("cuda:0")
     B, D, C, L, H = args.points, args.dims, args.channels, args.levels, 16
     pls = 2 ** (math.log2(2048 / H) / (L - 1))
@@ -125,7 +167,11 @@ def main(argv=None):
 
     peak, peak_src = hbm_peak()
     ev = lambda: torch.cuda.Event(enable_timing=True)
+    from bench import ClockSampler
+    x_host = (x.cpu() * 2 - 1).pin_memory()
     for name, ext in arms.items():
+        sampler = ClockSampler(0)
+        sampler.start()
         for _ in range(args.warmup):
             fwd(ext)
             bwd(ext)
@@ -154,6 +200,8 @@ def main(argv=None):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / args.steps
+        clocks = sampler.stop()
+        e2e = run_e2e(name, torch, ge, refext, x_host, emb, D, C, L, args.steps, args.warmup, dev)
         # algorithmic bytes: forward gathers 2^D rows of 4C bytes per (point, level),
         # writes 4C outputs + 4DC derivative; the backward zero-fills the gradient table, reads 4C upstream
         # gradient and reduces into 2^D rows (read-modify-write in L2: counted once, as a write), then
@@ -174,7 +222,9 @@ def main(argv=None):
                          "algorithmic_bytes": fwd_bytes,
                          "backward": {"algorithmic_bytes": bwd_bytes, "achieved": bwd_bytes / (ms_b * 1e-3) / 1e9,
                                       "frac": bwd_bytes / (ms_b * 1e-3) / 1e9 / peak}},
-            "parity_vs_reference": parity, "vs_baseline": None,
+            "parity_vs_reference": parity, "vs_baseline": None, "scaling": "weak", "clocks": clocks, "e2e": e2e,
+            # forward + scatter + input-gradient kernels of this library per step (the two memsets are torch's)
+            "gpu_launches": (0 if name == "reference" else (2 if name == "ours_fused" else 3)) * args.steps,
         }
         if name == "ours_fused":
             line["parity_vs_two_pass"] = fused_parity

@@ -35,3 +35,14 @@ def test_traffic_file_matches_default_workload():
     assert d["workload"] == bench.DEFAULT_WORKLOAD
     for k in ("blend_fwd", "blend_bwd"):
         assert d["kernels"][k]["dram_bytes"] > 1e8
+
+
+def test_grid_encoder_leg_refuses_to_run_without_cuda():
+    """bench.py --workload grid_encoder has no CPU path either."""
+    import torch
+    if torch.cuda.is_available():
+        return
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--workload", "grid_encoder"],
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode != 0
+    assert "no CUDA device" in json.loads(p.stdout.strip().splitlines()[-1])["error"]
