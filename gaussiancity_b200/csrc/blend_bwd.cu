@@ -310,5 +310,5 @@ cudaError_t gcr_launch_blend_bwd(const GcrBlendArgs& a, cudaStream_t stream) {
   static std::atomic<unsigned long long> configured{0ull};
   cudaError_t e = gcr_set_dynamic_smem_once(blend_bwd_kernel, kBwdSmemBytes, configured);
   if (e != cudaSuccess) return e;
-  return gcr_launch_chain(blend_bwd_kernel, grid, dim3(kBlendThreads), kBwdSmemBytes, stream, a);
+  return gcr_launch_chain<GCR_EDGE_BLEND_BWD>(blend_bwd_kernel, grid, dim3(kBlendThreads), kBwdSmemBytes, stream, a);
 }

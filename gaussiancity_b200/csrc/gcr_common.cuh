@@ -194,9 +194,12 @@ static inline cudaError_t gcr_set_dynamic_smem_once(Kernel kernel, int bytes, st
   return e;
 }
 
-// <<<>>> with the programmatic-stream-serialization attribute when PDL is on (gcr_pdl_enabled(), api.cu).
-bool gcr_pdl_enabled();
-template <typename... KArgs, typename... Args>
+// <<<>>> with the programmatic-stream-serialization attribute when PDL is on (gcr_pdl_edges(), api.cu).
+// Edge classes: the forward chain, the backward blend (its predecessor is a memset), the geometry backward
+// (its predecessor is the blend); all three are on when PDL is on (api.cu).
+enum { GCR_EDGE_FWD = 1, GCR_EDGE_BLEND_BWD = 2, GCR_EDGE_GEOM_BWD = 4 };
+int gcr_pdl_edges();   // bit mask of the edge classes launched programmatically (0 = PDL off)
+template <int kEdge = GCR_EDGE_FWD, typename... KArgs, typename... Args>
 static inline cudaError_t gcr_launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
                                            cudaStream_t stream, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
@@ -208,7 +211,7 @@ static inline cudaError_t gcr_launch_chain(void (*kernel)(KArgs...), dim3 grid, 
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = gcr_pdl_enabled() ? 1u : 0u;
+  cfg.numAttrs = (gcr_pdl_edges() & kEdge) != 0 ? 1u : 0u;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 #endif

@@ -484,5 +484,5 @@ cudaError_t gcr_launch_preprocess_bwd(const GcrPreprocessBwdArgs& a, cudaStream_
   void (*kernel)(GcrPreprocessBwdArgs) =
       big ? (sh ? preprocess_bwd_kernel<true, 8> : preprocess_bwd_kernel<false, 8>)
           : (sh ? preprocess_bwd_kernel<true, 1> : preprocess_bwd_kernel<false, 1>);
-  return gcr_launch_chain(kernel, dim3(blocks), dim3(256), 0, stream, a);
+  return gcr_launch_chain<GCR_EDGE_GEOM_BWD>(kernel, dim3(blocks), dim3(256), 0, stream, a);
 }

@@ -12,8 +12,11 @@ include/gcr_grid_encoder.h (libgcr_grid_encoder.so, csrc/grid_encoder.cu).  Ther
 a missing library raises, CPU tensors are refused.
 
 Differences from the reference that a caller can observe: embeddings must be float32 (the
-reference also dispatches half / double; GaussianCity never creates such a table); `fused_backward`
-(default off = the reference's two-pass backward through a stored dy_dx tensor).
+reference also dispatches half / double; GaussianCity never creates such a table); the module's
+`fused_backward` (default on: both gradients in one launch, no [B, L, D, C] derivative tensor --
+measured 0.231 vs 0.267 ms per forward + backward at the generator's size; the input gradient then
+agrees with the reference's to 1.5e-7 instead of bit for bit; off = the reference's two-pass
+backward through a stored dy_dx tensor, which is also what Seam A always does).
 """
 import ctypes
 import math
@@ -242,7 +245,7 @@ class GridEncoder(torch.nn.Module):
 
     def __init__(self, in_channels, n_levels, lvl_channels, desired_resolution, per_level_scale=2,
                  base_resolution=16, log2_hashmap_size=19, gridtype="hash", align_corners=False,
-                 fused_backward=False):
+                 fused_backward=True):
         super().__init__()
         self.in_channels = in_channels
         self.n_levels = n_levels

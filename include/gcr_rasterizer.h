@@ -264,7 +264,7 @@ GCR_API float gcr_profile_stage_ms(int stage);
  * griddepcontrol.wait, so results are unchanged, and the launch latency between them overlaps
  * the predecessor's tail -- what matters for frames of GaussianCity's own size (<= 16 384 points,
  * 13 kernels of 4-10 us).  Process-wide; on = 1 / off = 0; returns the previous setting.  The
- * initial value is GCR_PDL from the environment when set (0 / 1), else GCR_PDL_DEFAULT. */
+ * initial value is GCR_PDL from the environment when set (0 / 1), else on. */
 GCR_API int gcr_set_programmatic_launch(int on);
 
 #ifdef __cplusplus
