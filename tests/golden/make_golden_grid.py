@@ -80,7 +80,7 @@ def main(outdir):
             align_corners=np.int32(1 if c["align"] else 0), outputs=outputs.cpu().numpy(),
             dy_dx=dy_dx.cpu().numpy(), grad=grad.cpu().numpy(), grad_embeddings=ge.cpu().numpy(),
             grad_inputs=gi.cpu().numpy(), module_outputs=ym.detach().cpu().numpy(),
-            level_scales_torch_exp2=level_scales)
+            level_scales=level_scales)
         print(name, "outputs", tuple(outputs.shape), "table rows", int(enc.offsets[-1]))
 
 

@@ -109,11 +109,12 @@ def test_oracle_corner_rows_hash_and_dense():
 
 
 def device_level_scales(z):
-    """The level scales the GPU used, recovered from the golden outputs: exp2f on the device is
-    MUFU.EX2 (within 2 ulp of libm's correctly rounded value), everything else in the path is exactly
-    reproducible, so for each level exactly the right candidate makes the oracle's outputs equal the
-    reference's bit for bit.  Files written by the current make_golden_grid.py carry the device's own
-    values (`level_scales`) and the search is skipped."""
+    """The level scales the GPU used.  exp2f on the device is MUFU.EX2 based (within 2 ulp of libm's
+    correctly rounded value); everything else in the path is exactly reproducible.  The golden files carry
+    the device's own values (`level_scales`: torch.exp2 on the same GPU = the same CUDA routine the kernels
+    call -- checked to coincide, on all five cases, with the values recovered by the search below).  For a
+    file without them, each level's value is recovered from the outputs: exactly one of the 5 floats
+    within 2 ulp makes the oracle's outputs equal the reference's bit for bit."""
     if "level_scales" in z.files:
         return np.asarray(z["level_scales"], np.float32)
     pls, H = float(z["per_level_scale"]), int(z["base_resolution"])
@@ -284,3 +285,16 @@ def test_autograd_function_returns_one_gradient_per_argument(monkeypatch):
         assert calls[1][0] == ("bwd_fused" if calc and fused else "bwd") and calls[1][1] == (2, 4, 2)
     with pytest.raises(TypeError):
         ge.GridEncoderFunction.apply(torch.rand(4, 3), torch.rand(64, 2), offs, 2.0, 16, False, 0, False, False, 1)
+
+
+def test_recorded_level_scales_agree_with_recovery_from_outputs():
+    """The two ways of knowing the device's level scale -- recorded by the golden generator, recovered
+    from the reference outputs -- give the same floats (keeps the recovery path exercised)."""
+    path = [p for p in GOLDEN if p.endswith("hash_d4_c1.npz")][0]
+    z = np.load(path)
+    assert "level_scales" in z.files
+
+    class NoScales(dict):
+        files = [k for k in z.files if k != "level_scales"]
+    stripped = NoScales({k: z[k] for k in NoScales.files})
+    assert np.array_equal(device_level_scales(stripped), z["level_scales"])
