@@ -130,3 +130,12 @@ def test_argument_validation_returns_errors_without_touching_the_device(built_li
     assert bw < 0 and "single-stripe" in _cabi.last_error()
     assert l.gcr_stripe_partition(4, good, good, 1.0, good, None, good, good, 16, 16, 1.0, 1.0, 2, None, good, None) < 0
     assert l.gcr_peer_barrier(None, 0, 2, 1, None) < 0
+
+
+def test_programmatic_launch_switch_round_trips(built_lib):
+    """gcr_set_programmatic_launch returns the previous setting (host-side flag, no device)."""
+    from gaussiancity_b200 import _cabi
+    first = _cabi.set_programmatic_launch(False)
+    assert _cabi.set_programmatic_launch(True) is False
+    assert _cabi.set_programmatic_launch(first) is True
+    assert _cabi.set_programmatic_launch(first) is first
