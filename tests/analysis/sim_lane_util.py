@@ -1,4 +1,4 @@
-"""CPU-side design study (no GPU): how many survivor iterations would the blend kernels spend per warp
+"""CPU-side design study (no GPU; lives under tests/ because it drives the oracle, which is test infrastructure): how many survivor iterations would the blend kernels spend per warp
 for different pixel-group shapes?  Uses the C oracle's forward state for a bench workload, samples
 tiles, and replays the kernels' control flow in numpy:
 
@@ -12,7 +12,7 @@ Prints, per shape: mean evaluated iterations per warp, lane utilisation (contrib
 (pixel, record) pairs / (32 x iterations)) and the cull-test count, from which the expected issue
 slots per warp follow (EVAL ~ 50 and TEST ~ 25 SASS instructions, profiles/r01_ncu_full_v3).
 
-Usage: python tools/sim_lane_util.py [--workload cfg3_1M_sh3_1080p] [--tiles 200]
+Usage: python tests/analysis/sim_lane_util.py [--workload cfg3_1M_sh3_1080p] [--tiles 200]
 """
 import argparse
 import os
@@ -21,7 +21,7 @@ import time
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 
 
 def rect_touch(mx, my, A, B, C, twoL, rx0, rx1, ry0, ry1):
