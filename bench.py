@@ -532,6 +532,7 @@ def main():
             "vs_baseline": None}
     config = {"workload": args.workload, "gaussians": P, "image": f"{W}x{H}", "sh_degree": deg,
               "colour_path": "sh" if use_sh else "colors_precomp", "pass": "forward+backward",
+              "seed": 0, "timing": "mean over the K timed steps, one CUDA-event pair around them",
               "l2": "inputs (44+12M B/Gaussian = %.2f GB) exceed the 126 MB L2; no explicit flush"
                     % ((44 + (12 * (deg + 1) ** 2 if use_sh else 12)) * P / 1e9)}
 
