@@ -298,3 +298,36 @@ def test_recorded_level_scales_agree_with_recovery_from_outputs():
         files = [k for k in z.files if k != "level_scales"]
     stripped = NoScales({k: z[k] for k in NoScales.files})
     assert np.array_equal(device_level_scales(stripped), z["level_scales"])
+
+
+def test_oracle_properties_partition_of_unity_continuity_interpolation():
+    """Properties any 2^D-linear grid interpolation has, checked on the oracle independently of the
+    reference: (a) the corner weights sum to one -- a constant table encodes to that constant and its
+    input derivative vanishes; (b) the encoding is continuous across cell boundaries; (c) with
+    align_corners on a dense level, a point on a grid node returns that node's row exactly."""
+    D, C, L, H = 3, 2, 3, 4
+    offsets = go.level_offsets(D, L, H, 2, 12, False)
+    g = np.random.default_rng(5)
+    x = g.uniform(0, 1, (64, D)).astype(np.float32)
+    const = np.full((int(offsets[-1]), C), 0.75, np.float32)
+    out, dy_dx = go.forward(x, const, offsets, 2.0, H, True)
+    assert np.allclose(out, 0.75, atol=1e-6) and np.allclose(dy_dx, 0.0, atol=1e-4)
+    # (b) continuity: step across a cell boundary of the finest level along each axis
+    emb = g.uniform(-1, 1, (int(offsets[-1]), C)).astype(np.float32)
+    scale = float(go.level_scale(L - 1, 2.0, H))
+    for d in range(D):
+        a = np.full((1, D), 0.4321, np.float32)
+        a[0, d] = np.float32((7.0 - 0.5) / scale)           # pos = x * scale + 0.5 = 7: a boundary
+        lo, hi = a.copy(), a.copy()
+        lo[0, d] -= 1e-4
+        hi[0, d] += 1e-4
+        ol, _ = go.forward(lo, emb, offsets, 2.0, H)
+        oh, _ = go.forward(hi, emb, offsets, 2.0, H)
+        assert np.abs(ol - oh).max() < 5e-3                   # Lipschitz: |grad| <= 2 * scale * max|row| * 2e-4
+    # (c) align_corners: resolution = H * 2^level nodes per axis, node k at x = k / (resolution - 1)
+    offs = go.level_offsets(2, 1, 8, 2, 12, True)             # one dense 8 x 8 level
+    table = g.uniform(-1, 1, (int(offs[-1]), 2)).astype(np.float32)
+    nodes = np.array([[0.0, 0.0], [1.0, 1.0], [3 / 7, 5 / 7], [1.0, 0.0]], np.float32)
+    out, _ = go.forward(nodes, table, offs, 2.0, 8, False, 0, True)
+    idx = [0 + 0 * 8, 7 + 7 * 8, 3 + 5 * 8, 7 + 0 * 8]
+    assert np.allclose(out[0], table[idx], atol=2e-6)
