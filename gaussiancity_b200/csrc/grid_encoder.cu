@@ -429,7 +429,8 @@ int check_common(const float *inputs, const int *offsets, uint32_t B, uint32_t D
     if (D < 2 || D > 5 || !(C == 1 || C == 2 || C == 4 || C == 8)) return fail("GridEncoding: C must be 1, 2, 4, or 8.");
     if (!inputs || !offsets) return fail("gcr_grid: inputs / offsets must not be NULL");
     if (L == 0 || L > 65535u) return fail("gcr_grid: L must be in [1, 65535]");
-    if ((uint64_t)B * (C ? C : 1) >= (1ull << 32)) return fail("gcr_grid: B * C must be below 2^32");
+    // thread indices are 32-bit: B * C / min(C, 4) in the gather / scatter kernels, B * D in the input gradient
+    if ((uint64_t)B * (C > D ? C : D) >= (1ull << 32)) return fail("gcr_grid: B * max(C, D) must be below 2^32");
     return 0;
 }
 
